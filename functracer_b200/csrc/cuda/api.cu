@@ -1,0 +1,760 @@
+// api.cu — the C ABI of include/functracer_b200.h: scene upload, frame set-up, kernel launch,
+// tile assembly (blend / quantise), in-process multi-GPU with a P2P gather, statistics.
+//
+// There is NO CPU fallback in this file: without a CUDA device every entry point that computes
+// returns FTB_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../../include/functracer_b200.h"
+#include "device_scene.h"
+#include "lower.h"
+
+namespace ftb {
+
+// ---- assembly kernels (api.cu owns them; the render kernels live in render_f32/f64.cu) --------------
+constexpr int kMaxShards = 64;
+struct TilePtrs {
+    const void* p[kMaxShards];
+};
+
+template <typename R>
+__device__ __forceinline__ void loadTilePixel(const TilePtrs& bufs, int shard_count, int tiles_x, int x, int y, R& r, R& g, R& b)
+{
+    const int tile = (y / FTB_TILE_H) * tiles_x + (x / FTB_TILE_W);
+    const int shard = tile % shard_count, local = tile / shard_count;
+    const R* src = static_cast<const R*>(bufs.p[shard]) + 3 * ((long long)local * FTB_TILE_PIXELS + (y % FTB_TILE_H) * FTB_TILE_W + (x % FTB_TILE_W));
+    r = src[0]; g = src[1]; b = src[2];
+}
+
+// Image.write's toByte (Image.fs:36, Math.fs:12-16): clamp to [0,1], * 255.0, truncate.
+template <typename R>
+__device__ __forceinline__ unsigned char toByte(R c)
+{
+    R k = c > R(1) ? R(1) : (c < R(0) ? R(0) : c);  // NaN falls through both tests like Math.clamp
+    return (unsigned char)(int)(k * R(255));
+}
+
+// Tile-major shard buffers -> row-major frame.  corner = 1: CornerSampling.blendPixels
+// (Image.fs:134-144): pixel = average of the sample grid's [TL; TR; BL; BR] corners.
+template <typename R>
+__global__ void assemble_kernel(TilePtrs bufs, int shard_count, int tiles_x, int W, int H, int corner, int out_format, void* out)
+{
+    const long long n = (long long)W * H;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % W), y = (int)(i / W);
+        R r, g, b;
+        if (!corner) {
+            loadTilePixel<R>(bufs, shard_count, tiles_x, x, y, r, g, b);
+        } else {
+            R r1, g1, b1;
+            loadTilePixel<R>(bufs, shard_count, tiles_x, x, y, r, g, b);  // Seq.average: Zero + TL + TR + BL + BR, then / 4
+            r = R(0) + r; g = R(0) + g; b = R(0) + b;
+            loadTilePixel<R>(bufs, shard_count, tiles_x, x + 1, y, r1, g1, b1); r += r1; g += g1; b += b1;
+            loadTilePixel<R>(bufs, shard_count, tiles_x, x, y + 1, r1, g1, b1); r += r1; g += g1; b += b1;
+            loadTilePixel<R>(bufs, shard_count, tiles_x, x + 1, y + 1, r1, g1, b1); r += r1; g += g1; b += b1;
+            r = r / R(4); g = g / R(4); b = b / R(4);
+        }
+        if (out_format == FTB_OUT_RGB_F64) {
+            double* o = static_cast<double*>(out) + 3 * i;
+            o[0] = (double)r; o[1] = (double)g; o[2] = (double)b;
+        } else if (out_format == FTB_OUT_RGB_F32) {
+            float* o = static_cast<float*>(out) + 3 * i;
+            o[0] = (float)r; o[1] = (float)g; o[2] = (float)b;
+        } else {
+            static_cast<uchar4*>(out)[i] = make_uchar4(toByte(r), toByte(g), toByte(b), 255);
+        }
+    }
+}
+
+// ftb_shade_rays: [ray][3] in R -> doubles
+template <typename R>
+__global__ void widen_kernel(const R* in, double* out, long long n)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) out[i] = (double)in[i];
+}
+
+}  // namespace ftb
+
+namespace {
+
+using namespace ftb;
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg)
+{
+    g_err = msg;
+    return code;
+}
+int cudaFail(cudaError_t e, const char* what)
+{
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    (void)cudaGetLastError();
+    return e == cudaErrorMemoryAllocation ? FTB_ERR_OOM : FTB_ERR_CUDA;
+}
+#define CK(expr)                                              \
+    do {                                                      \
+        cudaError_t e__ = (expr);                             \
+        if (e__ != cudaSuccess) return cudaFail(e__, #expr); \
+    } while (0)
+
+// A growable device buffer (scratch that survives between calls so steady-state frames do no cudaMalloc).
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct Control {  // device control block of one launch
+    unsigned int tile_counter;
+    unsigned int overflow;
+    unsigned long long stats[ST_COUNT];
+};
+
+template <typename R>
+struct SceneStorage {
+    DevScene<R> view;
+    std::vector<void*> allocs;
+    bool ready = false;
+    void release() { for (void* p : allocs) cudaFree(p); allocs.clear(); ready = false; }
+};
+
+struct PerDevice;
+template <typename R> SceneStorage<R>& storageOf(PerDevice* pd);
+
+struct PerDevice {
+    int device = -1;
+    int sm_count = 0;
+    SceneStorage<float> f32;
+    SceneStorage<double> f64;
+    cudaStream_t stream = nullptr;  // owned; used by the host-buffer entry points
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, done = nullptr;
+    DevBuf control, jitter, tiles, out, dbg_prim, dbg_sub, dbg_t, rays;
+    std::vector<DevBuf> peer_tiles;  // on the gather device: one per remote shard
+};
+
+template <> SceneStorage<float>& storageOf<float>(PerDevice* pd) { return pd->f32; }
+template <> SceneStorage<double>& storageOf<double>(PerDevice* pd) { return pd->f64; }
+
+}  // namespace
+
+struct ftb_scene {
+    ftb::Lowered L;
+    // host copies of the tables the upload needs
+    std::vector<ftb_bsp_node> bsp_nodes;
+    std::vector<ftb_bsp_leaf> bsp_leaves;
+    std::vector<ftb_mesh> meshes;
+    std::vector<double> triangles;
+    std::vector<ftb_light> lights;
+    struct Img { int w, h; std::vector<uint8_t> rgb; };
+    std::vector<Img> images;
+    std::map<int, std::unique_ptr<PerDevice>> devices;
+};
+
+namespace {
+
+template <typename R> struct Mk4;
+template <> struct Mk4<float> { static float4 make(double a, double b, double c, double d) { return make_float4((float)a, (float)b, (float)c, (float)d); } };
+template <> struct Mk4<double> { static double4 make(double a, double b, double c, double d) { return make_double4(a, b, c, d); } };
+
+template <typename T>
+int upload(std::vector<void*>& allocs, const std::vector<T>& host, const T*& dev)
+{
+    dev = nullptr;
+    if (host.empty()) return FTB_OK;
+    void* p = nullptr;
+    CK(cudaMalloc(&p, host.size() * sizeof(T)));
+    allocs.push_back(p);
+    CK(cudaMemcpy(p, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+    dev = static_cast<const T*>(p);
+    return FTB_OK;
+}
+
+template <typename R>
+int uploadScene(const ftb_scene& sc, SceneStorage<R>& st)
+{
+    typedef typename V4<R>::type R4;
+    const Lowered& L = sc.L;
+    DevScene<R>& v = st.view;
+    std::memset(&v, 0, sizeof(v));
+    int rc;
+#define UP(vec, field) if ((rc = upload(st.allocs, vec, field)) != FTB_OK) return rc;
+    {
+        std::vector<R4> w2m; std::vector<int4> meta;
+        for (const Leaf& lf : L.leaves) {
+            for (int r = 0; r < 3; ++r) w2m.push_back(Mk4<R>::make(lf.w2m[4 * r], lf.w2m[4 * r + 1], lf.w2m[4 * r + 2], lf.w2m[4 * r + 3]));
+            meta.push_back(make_int4(lf.kind | (lf.identity << 8), lf.surface, lf.prim, lf.payload));
+        }
+        UP(w2m, v.leaf_w2m) UP(meta, v.leaf_meta)
+        v.n_leaves = (int)L.leaves.size();
+    }
+    {
+        std::vector<int4> items; std::vector<R4> bounds; std::vector<int2> ops;
+        for (const Item& it : L.items) {
+            items.push_back(make_int4(it.kind, it.a, it.b, it.casts_shadow));
+            bounds.push_back(Mk4<R>::make(it.bound_c[0], it.bound_c[1], it.bound_c[2], it.bound_r));
+        }
+        for (const CsgOp& op : L.ops) ops.push_back(make_int2(op.kind, op.arg));
+        UP(items, v.items) UP(bounds, v.item_bound) UP(ops, v.ops)
+        v.n_items = (int)L.items.size();
+    }
+    {
+        std::vector<R4> a, b; std::vector<int4> si;
+        for (const Surface& s : L.surfaces) {
+            a.push_back(Mk4<R>::make(s.colour[0], s.colour[1], s.colour[2], s.roughness));
+            b.push_back(Mk4<R>::make(s.reflectance, s.shineyness, 0, 0));
+            si.push_back(make_int4(s.texture, s.hue, s.apply_lighting, 0));
+        }
+        UP(a, v.surf_a) UP(b, v.surf_b) UP(si, v.surf_i)
+    }
+    {
+        std::vector<int4> ti; std::vector<R4> c1, c2; std::vector<int> kinds; std::vector<R> ab;
+        for (const TexDef& t : L.textures) {
+            ti.push_back(make_int4(t.op_first, t.op_count, t.base_kind, t.image));
+            c1.push_back(Mk4<R>::make(t.c1[0], t.c1[1], t.c1[2], 0));
+            c2.push_back(Mk4<R>::make(t.c2[0], t.c2[1], t.c2[2], 0));
+        }
+        for (const TexOp& o : L.tex_ops) { kinds.push_back(o.kind); ab.push_back((R)o.a); ab.push_back((R)o.b); }
+        UP(ti, v.tex_i) UP(c1, v.tex_c1) UP(c2, v.tex_c2) UP(kinds, v.texop_kind) UP(ab, v.texop_ab)
+        std::vector<uchar4> texels; std::vector<int4> ii;
+        for (const ftb_scene::Img& im : sc.images) {
+            ii.push_back(make_int4((int)texels.size(), im.w, im.h, 0));
+            const size_t n = (size_t)im.w * im.h;
+            for (size_t k = 0; k < n; ++k) texels.push_back(make_uchar4(im.rgb[3 * k], im.rgb[3 * k + 1], im.rgb[3 * k + 2], 255));
+        }
+        UP(texels, v.texels) UP(ii, v.img_i)
+    }
+    {
+        std::vector<int> roots; std::vector<R> aabb; std::vector<int2> links, leaves; std::vector<R4> tris;
+        for (const ftb_mesh& m : sc.meshes) roots.push_back(m.root);
+        for (const ftb_bsp_node& n : sc.bsp_nodes) {
+            for (int k = 0; k < 3; ++k) aabb.push_back((R)n.aabb_min[k]);
+            for (int k = 0; k < 3; ++k) aabb.push_back((R)n.aabb_max[k]);
+            links.push_back(make_int2(n.left, n.right));
+        }
+        for (const ftb_bsp_leaf& l : sc.bsp_leaves) leaves.push_back(make_int2(l.tri_first, l.tri_count));
+        const size_t nt = sc.triangles.size() / 9;
+        for (size_t t = 0; t < nt; ++t) {  // v0, e1 = v1 - v0, e2 = v2 - v0 (Triangle.fs:45-46), differences taken in double
+            const double* q = sc.triangles.data() + 9 * t;
+            tris.push_back(Mk4<R>::make(q[0], q[1], q[2], 0));
+            tris.push_back(Mk4<R>::make(q[3] - q[0], q[4] - q[1], q[5] - q[2], 0));
+            tris.push_back(Mk4<R>::make(q[6] - q[0], q[7] - q[1], q[8] - q[2], 0));
+        }
+        UP(roots, v.mesh_root) UP(aabb, v.bsp_aabb) UP(links, v.bsp_links) UP(leaves, v.bsp_leaves) UP(tris, v.tris)
+    }
+    {
+        std::vector<int2> li; std::vector<R4> la, lb, lc;
+        for (const ftb_light& l : sc.lights) {
+            li.push_back(make_int2(l.kind, l.samples));
+            la.push_back(Mk4<R>::make(l.v[0], l.v[1], l.v[2], std::tan(l.scatter_rad / 2.0)));  // Jitter.fs:29
+            lb.push_back(Mk4<R>::make(l.falloff[0], l.falloff[1], l.falloff[2], 0));
+            lc.push_back(Mk4<R>::make(l.colour[0], l.colour[1], l.colour[2], 0));
+        }
+        UP(li, v.light_i) UP(la, v.light_a) UP(lb, v.light_b) UP(lc, v.light_c)
+        v.n_lights = (int)sc.lights.size();
+    }
+#undef UP
+    st.ready = true;
+    return FTB_OK;
+}
+
+int getDevice(ftb_scene* sc, int device, PerDevice** out)
+{
+    auto it = sc->devices.find(device);
+    if (it == sc->devices.end()) {
+        std::unique_ptr<PerDevice> pd(new PerDevice);
+        pd->device = device;
+        CK(cudaSetDevice(device));
+        CK(cudaDeviceGetAttribute(&pd->sm_count, cudaDevAttrMultiProcessorCount, device));
+        CK(cudaStreamCreateWithFlags(&pd->stream, cudaStreamNonBlocking));
+        CK(cudaEventCreate(&pd->ev0));
+        CK(cudaEventCreate(&pd->ev1));
+        CK(cudaEventCreateWithFlags(&pd->done, cudaEventDisableTiming));
+        it = sc->devices.emplace(device, std::move(pd)).first;
+    }
+    *out = it->second.get();
+    return FTB_OK;
+}
+
+struct FrameGeom {
+    int gw, gh, spp, tiles_x, tiles_y, n_tiles, shard_index, shard_count, n_local_tiles;
+    long long n_samples;
+    bool corner;
+};
+
+int frameGeom(const ftb_render_params* p, FrameGeom& g)
+{
+    if (!p) return fail(FTB_ERR_BAD_ARG, "null params");
+    if (p->width < 1 || p->height < 1) return fail(FTB_ERR_BAD_ARG, "bad resolution");
+    if ((long long)p->width * p->height > (1LL << 30)) return fail(FTB_ERR_BAD_ARG, "resolution too large");
+    if (p->sampling != FTB_SAMPLING_JITTER && p->sampling != FTB_SAMPLING_CORNER) return fail(FTB_ERR_BAD_ARG, "bad sampling mode");
+    if (p->precision != FTB_PRECISION_FP32 && p->precision != FTB_PRECISION_FP64_VERIFY) return fail(FTB_ERR_BAD_ARG, "bad precision");
+    if (p->out_format < FTB_OUT_RGB_F64 || p->out_format > FTB_OUT_RGBA8) return fail(FTB_ERR_BAD_ARG, "bad output format");
+    g.corner = p->sampling == FTB_SAMPLING_CORNER;
+    if (!g.corner && (p->spp < 1 || !p->jitter_xy)) return fail(FTB_ERR_BAD_ARG, "jitter mode needs spp >= 1 and jitter_xy");
+    g.gw = g.corner ? p->width + 1 : p->width;
+    g.gh = g.corner ? p->height + 1 : p->height;
+    g.spp = g.corner ? 1 : p->spp;
+    g.tiles_x = (g.gw + FTB_TILE_W - 1) / FTB_TILE_W;
+    g.tiles_y = (g.gh + FTB_TILE_H - 1) / FTB_TILE_H;
+    g.n_tiles = g.tiles_x * g.tiles_y;
+    g.shard_count = p->shard_count > 1 ? p->shard_count : 1;
+    g.shard_index = p->shard_count > 1 ? p->shard_index : 0;
+    if (g.shard_count > kMaxShards) return fail(FTB_ERR_BAD_ARG, "shard_count exceeds 64");
+    if (g.shard_index < 0 || g.shard_index >= g.shard_count) return fail(FTB_ERR_BAD_ARG, "shard_index out of range");
+    g.n_local_tiles = (g.n_tiles - g.shard_index + g.shard_count - 1) / g.shard_count;
+    g.n_samples = (long long)g.gw * g.gh * g.spp;
+    return FTB_OK;
+}
+
+inline size_t realSize(int precision) { return precision == FTB_PRECISION_FP64_VERIFY ? sizeof(double) : sizeof(float); }
+
+struct V3 { double x, y, z; };
+inline V3 sub(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline V3 cross(V3 a, V3 b) { return {a.y * b.z - a.z * b.y, b.x * a.z - b.z * a.x, a.x * b.y - a.y * b.x}; }
+inline V3 normalise(V3 v)
+{
+    double l = std::sqrt(v.x * v.x + v.y * v.y + v.z * v.z);
+    if (l < 0.0000001) return v;
+    double s = 1.0 / l;
+    return {s * v.x, s * v.y, s * v.z};
+}
+
+// ImagePlane.create / fromCamera (Image.fs:48-53, 67-81), evaluated in double on the host; the
+// FP32 kernels receive the narrowed results.
+template <typename R>
+void fillCamera(DevFrame<R>& F, const ftb_camera& c, int resH, int resV)
+{
+    V3 o = {c.o[0], c.o[1], c.o[2]}, la = {c.look_at[0], c.look_at[1], c.look_at[2]}, up = {c.up[0], c.up[1], c.up[2]};
+    V3 k = normalise(sub(la, o));
+    V3 i = normalise(cross(up, k));
+    V3 j = cross(k, i);
+    double height = std::tan(c.fov_y_rad / 2.0) * 2.0;
+    double width = height * c.aspect_ratio;
+    double pixelHeight = height / (double)(resH - 1);  // the reference's swapped axes (Image.fs:71-72)
+    double pixelWidth = width / (double)(resV - 1);
+    F.cam_o[0] = (R)o.x; F.cam_o[1] = (R)o.y; F.cam_o[2] = (R)o.z;
+    F.cam_k[0] = (R)k.x; F.cam_k[1] = (R)k.y; F.cam_k[2] = (R)k.z;
+    F.cam_i[0] = (R)i.x; F.cam_i[1] = (R)i.y; F.cam_i[2] = (R)i.z;
+    F.cam_j[0] = (R)j.x; F.cam_j[1] = (R)j.y; F.cam_j[2] = (R)j.z;
+    F.pw = (R)pixelWidth; F.ph = (R)pixelHeight;
+    F.tlx = (R)(-width / 2.0 + pixelWidth / 2.0);
+    F.tly = (R)(height / 2.0 - pixelHeight / 2.0);
+    F.has_focus = c.has_focus;
+    F.focal = (R)c.focal_length;
+    F.tan_half_aperture = (R)std::tan(c.aperture_rad / 2.0);
+}
+
+void fillStats(const Control& h, const ftb_scene& sc, ftb_stats* s)
+{
+    const unsigned long long* c = h.stats;
+    s->primary_rays += c[ST_PRIMARY]; s->shadow_rays += c[ST_SHADOW]; s->reflection_rays += c[ST_REFLECTION]; s->shaded_hits += c[ST_SHADED];
+    // device leaf kinds -> ftb_prim_kind slots.  The parts of a solidCylinder are counted as what
+    // they are on the device (2 circles + 1 open cylinder); a cube is one fused leaf.
+    static const int slot[9] = {FTB_PRIM_SPHERE, FTB_PRIM_PLANE, FTB_PRIM_SQUARE, FTB_PRIM_CIRCLE, FTB_PRIM_CYLINDER, FTB_PRIM_CONE, FTB_PRIM_CUBE, FTB_PRIM_TRIANGLE, FTB_PRIM_BSPMESH};
+    for (int k = 0; k < 9; ++k) s->leaf_tests[slot[k]] += c[ST_LEAF0 + k];
+    s->leaf_tests[FTB_PRIM_TRIANGLE] += c[ST_TRI_TESTS_IN_MESH];
+    s->transformed_leaf_tests += c[ST_XFORM]; s->bsp_nodes_visited += c[ST_BSP_NODES]; s->bound_tests += c[ST_BOUND_TESTS]; s->csg_ops += c[ST_CSG_OPS];
+    // algorithmic flops, SURVEY.md 8(d) table (FMA = 2; compares / selects = 0)
+    static const double F[9] = {28, 8, 8, 8, 26, 32, 20, 45, 0};
+    double f = 0;
+    for (int k = 0; k < 9; ++k) f += F[k] * (double)c[ST_LEAF0 + k];
+    f += 45.0 * (double)c[ST_TRI_TESTS_IN_MESH] + 33.0 * (double)c[ST_XFORM] + 12.0 * (double)c[ST_BSP_NODES] + 28.0 * (double)c[ST_BOUND_TESTS];
+    f += (double)c[ST_SHADED] * (60.0 + 110.0 * (double)sc.lights.size()) + 18.0 * (double)c[ST_REFLECTION];
+    s->flops += f;
+}
+
+// Renders one shard's tiles (mode 0) on the CURRENT device into d_tiles.  Everything is queued on
+// `stream`; nothing here synchronises unless stats are requested.
+template <typename R>
+int launchFrame(ftb_scene* sc, PerDevice* pd, const ftb_camera* cam, const ftb_render_params* p, const FrameGeom& g, void* d_tiles,
+                const ftb_debug_out* d_dbg, ftb_stats* stats, cudaStream_t stream, bool timeKernel)
+{
+    SceneStorage<R>& st = storageOf<R>(pd);
+    if (!st.ready) { int rc = uploadScene<R>(*sc, st); if (rc != FTB_OK) return rc; }
+    CK(pd->control.reserve(sizeof(Control)));
+    CK(cudaMemsetAsync(pd->control.p, 0, sizeof(Control), stream));
+    DevFrame<R> F;
+    std::memset(&F, 0, sizeof(F));
+    F.mode = 0;
+    F.gw = g.gw; F.gh = g.gh; F.spp = g.spp; F.tiles_x = g.tiles_x;
+    F.n_local_tiles = g.n_local_tiles; F.shard_index = g.shard_index; F.shard_count = g.shard_count;
+    fillCamera<R>(F, *cam, p->width, p->height);
+    if (!g.corner) {
+        std::vector<R> j(2 * (size_t)g.spp);
+        for (size_t k = 0; k < j.size(); ++k) j[k] = (R)p->jitter_xy[k];
+        CK(pd->jitter.reserve(j.size() * sizeof(R)));
+        CK(cudaMemcpyAsync(pd->jitter.p, j.data(), j.size() * sizeof(R), cudaMemcpyHostToDevice, stream));  // pageable source: staged before return
+        F.jitter = static_cast<const R*>(pd->jitter.p);
+    } else {
+        // CornerSampling.generateRays (Image.fs:128-132): every corner ray uses the offset (-0.5, +0.5)
+        const R j[2] = {R(-0.5), R(0.5)};
+        CK(pd->jitter.reserve(sizeof(j)));
+        CK(cudaMemcpyAsync(pd->jitter.p, j, sizeof(j), cudaMemcpyHostToDevice, stream));
+        F.jitter = static_cast<const R*>(pd->jitter.p);
+    }
+    F.recursion_limit = p->recursion_limit;
+    F.seed = p->seed;
+    F.out = static_cast<R*>(d_tiles);
+    if (d_dbg) { F.dbg_prim = d_dbg->prim_id; F.dbg_sub = d_dbg->sub_id; F.dbg_t = d_dbg->t; }
+    Control* ctl = static_cast<Control*>(pd->control.p);
+    F.tile_counter = &ctl->tile_counter; F.overflow = &ctl->overflow; F.stats = ctl->stats;
+    const bool wantStats = stats && p->collect_stats;
+    if (timeKernel) CK(cudaEventRecord(pd->ev0, stream));
+    int launches = 0;
+    CK(launch_render<R>(st.view, F, wantStats, pd->sm_count, stream, &launches));
+    if (timeKernel) CK(cudaEventRecord(pd->ev1, stream));
+    if (stats) stats->kernel_launches += launches + 1;  // + the control-block memset
+    return FTB_OK;
+}
+
+int launchFrameAny(ftb_scene* sc, PerDevice* pd, const ftb_camera* cam, const ftb_render_params* p, const FrameGeom& g, void* d_tiles,
+                   const ftb_debug_out* d_dbg, ftb_stats* stats, cudaStream_t stream, bool timeKernel)
+{
+    if (p->precision == FTB_PRECISION_FP64_VERIFY) return launchFrame<double>(sc, pd, cam, p, g, d_tiles, d_dbg, stats, stream, timeKernel);
+    return launchFrame<float>(sc, pd, cam, p, g, d_tiles, d_dbg, stats, stream, timeKernel);
+}
+
+// Reads the control block back (synchronises the stream) and folds it into stats.
+int finishStats(ftb_scene* sc, PerDevice* pd, ftb_stats* stats, cudaStream_t stream, bool timed, bool* overflow)
+{
+    Control h;
+    CK(cudaMemcpyAsync(&h, pd->control.p, sizeof(h), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    if (h.overflow) *overflow = true;
+    if (stats) {
+        fillStats(h, *sc, stats);
+        if (h.overflow) stats->hit_overflow = 1;
+        if (timed) { float ms = 0; CK(cudaEventElapsedTime(&ms, pd->ev0, pd->ev1)); if ((double)ms > stats->kernel_ms) stats->kernel_ms = ms; }
+    }
+    return FTB_OK;
+}
+
+int launchAssemble(const ftb_render_params* p, const FrameGeom& g, const void* const* bufs, void* d_out, cudaStream_t stream)
+{
+    TilePtrs tp;
+    std::memset(&tp, 0, sizeof(tp));
+    for (int i = 0; i < g.shard_count; ++i) tp.p[i] = bufs[i];
+    const long long n = (long long)p->width * p->height;
+    int grid = (int)std::min<long long>((n + 255) / 256, 148 * 16);
+    if (p->precision == FTB_PRECISION_FP64_VERIFY)
+        assemble_kernel<double><<<grid, 256, 0, stream>>>(tp, g.shard_count, g.tiles_x, p->width, p->height, g.corner ? 1 : 0, p->out_format, d_out);
+    else
+        assemble_kernel<float><<<grid, 256, 0, stream>>>(tp, g.shard_count, g.tiles_x, p->width, p->height, g.corner ? 1 : 0, p->out_format, d_out);
+    CK(cudaGetLastError());
+    return FTB_OK;
+}
+
+inline size_t outBytes(const ftb_render_params* p)
+{
+    const size_t n = (size_t)p->width * p->height;
+    return p->out_format == FTB_OUT_RGB_F64 ? n * 24 : (p->out_format == FTB_OUT_RGB_F32 ? n * 12 : n * 4);
+}
+
+struct DeviceRestore {
+    int dev = -1;
+    DeviceRestore() { if (cudaGetDevice(&dev) != cudaSuccess) dev = -1; }
+    ~DeviceRestore() { if (dev >= 0) cudaSetDevice(dev); }
+};
+
+}  // namespace
+
+extern "C" {
+
+int ftb_abi_version(void) { return FTB_ABI_VERSION; }
+
+int ftb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int d = 0; d < n; ++d) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) ++ok;
+    }
+    return ok;
+}
+
+const char* ftb_last_error(void) { return g_err.c_str(); }
+
+int ftb_scene_create(const ftb_scene_desc* desc, ftb_scene** out)
+{
+    if (!desc || !out) return fail(FTB_ERR_BAD_ARG, "null argument");
+    *out = nullptr;
+    std::unique_ptr<ftb_scene> sc(new ftb_scene);
+    std::string err;
+    int rc = ftb::lower_scene(*desc, sc->L, err);
+    if (rc != FTB_OK) return fail(rc, err);
+    if (sc->L.max_csg_lists > ftb::kMaxLists) return fail(FTB_ERR_UNSUPPORTED, "CSG nesting needs more than 12 pending hit lists");
+    if (sc->L.max_bsp_depth + 1 > ftb::kBspStack) return fail(FTB_ERR_UNSUPPORTED, "BSP tree deeper than the 64-entry traversal stack");
+    if (sc->L.leaves.size() >= (1u << 22)) return fail(FTB_ERR_UNSUPPORTED, "more than 4M leaves");
+    sc->bsp_nodes.assign(desc->bsp_nodes, desc->bsp_nodes + desc->n_bsp_nodes);
+    sc->bsp_leaves.assign(desc->bsp_leaves, desc->bsp_leaves + desc->n_bsp_leaves);
+    sc->meshes.assign(desc->meshes, desc->meshes + desc->n_meshes);
+    sc->triangles.assign(desc->triangles, desc->triangles + 9 * (size_t)desc->n_triangles);
+    sc->lights.assign(desc->lights, desc->lights + desc->n_lights);
+    for (int i = 0; i < desc->n_images; ++i) {
+        ftb_scene::Img im;
+        im.w = desc->images[i].width; im.h = desc->images[i].height;
+        if (desc->images[i].rgb24 && im.w > 0 && im.h > 0) im.rgb.assign(desc->images[i].rgb24, desc->images[i].rgb24 + 3 * (size_t)im.w * im.h);
+        else { im.w = im.h = 1; im.rgb.assign(3, 0); }
+        sc->images.push_back(std::move(im));
+    }
+    // upload to the current device now, so that create fails loudly without a GPU
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n < 1) { (void)cudaGetLastError(); return fail(FTB_ERR_NO_DEVICE, "no CUDA device: functracer_b200 has no CPU path"); }
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    PerDevice* pd = nullptr;
+    rc = getDevice(sc.get(), dev, &pd);
+    if (rc != FTB_OK) return rc;
+    rc = uploadScene<float>(*sc, pd->f32);
+    if (rc != FTB_OK) return rc;
+    *out = sc.release();
+    return FTB_OK;
+}
+
+void ftb_scene_destroy(ftb_scene* sc)
+{
+    if (!sc) return;
+    DeviceRestore restore;
+    for (auto& kv : sc->devices) {
+        PerDevice* pd = kv.second.get();
+        cudaSetDevice(pd->device);
+        if (pd->stream) cudaStreamSynchronize(pd->stream);
+        pd->f32.release(); pd->f64.release();
+        for (DevBuf* b : {&pd->control, &pd->jitter, &pd->tiles, &pd->out, &pd->dbg_prim, &pd->dbg_sub, &pd->dbg_t, &pd->rays}) b->release();
+        for (DevBuf& b : pd->peer_tiles) b.release();
+        if (pd->ev0) cudaEventDestroy(pd->ev0);
+        if (pd->ev1) cudaEventDestroy(pd->ev1);
+        if (pd->done) cudaEventDestroy(pd->done);
+        if (pd->stream) cudaStreamDestroy(pd->stream);
+    }
+    delete sc;
+}
+
+int64_t ftb_tile_buffer_bytes(const ftb_render_params* params)
+{
+    FrameGeom g;
+    int rc = frameGeom(params, g);
+    if (rc != FTB_OK) return rc;
+    return (int64_t)g.n_local_tiles * FTB_TILE_PIXELS * 3 * (int64_t)realSize(params->precision);
+}
+
+int ftb_render_tiles_device(ftb_scene* scene, const ftb_camera* camera, const ftb_render_params* params, void* d_tiles,
+                            const ftb_debug_out* d_dbg, ftb_stats* stats, void* stream)
+{
+    if (!scene || !camera || !params || !d_tiles) return fail(FTB_ERR_BAD_ARG, "null argument");
+    FrameGeom g;
+    int rc = frameGeom(params, g);
+    if (rc != FTB_OK) return rc;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); return fail(FTB_ERR_NO_DEVICE, "no CUDA device"); }
+    PerDevice* pd = nullptr;
+    if ((rc = getDevice(scene, dev, &pd)) != FTB_OK) return rc;
+    if (stats) std::memset(stats, 0, sizeof(*stats));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if ((rc = launchFrameAny(scene, pd, camera, params, g, d_tiles, d_dbg, stats, s, stats != nullptr)) != FTB_OK) return rc;
+    if (stats) {  // the only synchronising path of this entry point
+        bool overflow = false;
+        if ((rc = finishStats(scene, pd, stats, s, true, &overflow)) != FTB_OK) return rc;
+        if (overflow) return fail(FTB_ERR_HIT_OVERFLOW, "a CSG operand produced more than 32 crossings on one ray");
+    }
+    return FTB_OK;
+}
+
+int ftb_assemble_device(const ftb_render_params* params, const void* const* d_tile_buffers, void* d_out, void* stream)
+{
+    if (!params || !d_tile_buffers || !d_out) return fail(FTB_ERR_BAD_ARG, "null argument");
+    FrameGeom g;
+    int rc = frameGeom(params, g);
+    if (rc != FTB_OK) return rc;
+    for (int i = 0; i < g.shard_count; ++i)
+        if (!d_tile_buffers[i]) return fail(FTB_ERR_BAD_ARG, "null tile buffer");
+    return launchAssemble(params, g, d_tile_buffers, d_out, static_cast<cudaStream_t>(stream));
+}
+
+int ftb_render(ftb_scene* scene, const ftb_camera* camera, const ftb_render_params* params, void* out, const ftb_debug_out* dbg, ftb_stats* stats)
+{
+    const auto t0 = std::chrono::steady_clock::now();
+    if (!scene || !camera || !params || !out) return fail(FTB_ERR_BAD_ARG, "null argument");
+    FrameGeom full;
+    ftb_render_params p = *params;
+    int rc = frameGeom(&p, full);
+    if (rc != FTB_OK) return rc;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { (void)cudaGetLastError(); return fail(FTB_ERR_NO_DEVICE, "no CUDA device: functracer_b200 has no CPU path"); }
+    if (stats) std::memset(stats, 0, sizeof(*stats));
+    DeviceRestore restore;
+    const int n_gpus = p.n_gpus > 1 ? p.n_gpus : 1;
+    if (n_gpus > ndev) return fail(FTB_ERR_NO_DEVICE, "n_gpus exceeds the visible devices");
+    if (n_gpus > 1 && p.shard_count > 1) return fail(FTB_ERR_BAD_ARG, "n_gpus > 1 cannot be combined with an external shard");
+    if (n_gpus > 1 && dbg) return fail(FTB_ERR_UNSUPPORTED, "debug planes need n_gpus <= 1");
+    if (full.shard_count > 1 && n_gpus == 1) {
+        // a single external shard cannot be assembled into a frame: the caller wants ftb_render_tiles_device
+        return fail(FTB_ERR_BAD_ARG, "ftb_render renders whole frames; use ftb_render_tiles_device for one shard");
+    }
+    const size_t rs = realSize(p.precision);
+    std::vector<PerDevice*> pds(n_gpus);
+    std::vector<const void*> bufs(n_gpus);
+    const int primary = n_gpus > 1 ? 0 : restore.dev;
+    // ---- render: one shard per device, all queued before anything is waited on ----------------------
+    for (int k = 0; k < n_gpus; ++k) {
+        const int dev = n_gpus > 1 ? k : primary;
+        CK(cudaSetDevice(dev));
+        if ((rc = getDevice(scene, dev, &pds[k])) != FTB_OK) return rc;
+        PerDevice* pd = pds[k];
+        ftb_render_params ps = p;
+        ps.shard_index = k; ps.shard_count = n_gpus;
+        FrameGeom g;
+        if ((rc = frameGeom(&ps, g)) != FTB_OK) return rc;
+        const size_t tileBytes = (size_t)g.n_local_tiles * FTB_TILE_PIXELS * 3 * rs;
+        CK(pd->tiles.reserve(tileBytes));
+        ftb_debug_out ddbg = {nullptr, nullptr, nullptr};
+        if (dbg && dbg->prim_id) {
+            CK(pd->dbg_prim.reserve((size_t)full.n_samples * 4));
+            CK(cudaMemsetAsync(pd->dbg_prim.p, 0xff, (size_t)full.n_samples * 4, pd->stream));
+            ddbg.prim_id = static_cast<int32_t*>(pd->dbg_prim.p);
+            if (dbg->sub_id) { CK(pd->dbg_sub.reserve((size_t)full.n_samples * 4)); CK(cudaMemsetAsync(pd->dbg_sub.p, 0, (size_t)full.n_samples * 4, pd->stream)); ddbg.sub_id = static_cast<int32_t*>(pd->dbg_sub.p); }
+            if (dbg->t) { CK(pd->dbg_t.reserve((size_t)full.n_samples * 8)); CK(cudaMemsetAsync(pd->dbg_t.p, 0, (size_t)full.n_samples * 8, pd->stream)); ddbg.t = static_cast<double*>(pd->dbg_t.p); }
+        }
+        if ((rc = launchFrameAny(scene, pd, camera, &ps, g, pd->tiles.p, ddbg.prim_id ? &ddbg : nullptr, stats, pd->stream, stats != nullptr)) != FTB_OK) return rc;
+        bufs[k] = pd->tiles.p;
+        if (k > 0) {  // gather over NVLink: peer copy into a staging buffer on the primary device
+            PerDevice* p0 = pds[0];
+            if ((int)p0->peer_tiles.size() < n_gpus) p0->peer_tiles.resize(n_gpus);
+            CK(cudaSetDevice(primary));
+            CK(p0->peer_tiles[k].reserve(tileBytes));
+            CK(cudaSetDevice(dev));
+            {  // direct NVLink path; without peer access the copy would be staged through the host
+                cudaError_t pe = cudaDeviceEnablePeerAccess(primary, 0);
+                if (pe != cudaSuccess) (void)cudaGetLastError();  // already enabled / unsupported: the copy still works
+            }
+            CK(cudaMemcpyPeerAsync(p0->peer_tiles[k].p, primary, pd->tiles.p, dev, tileBytes, pd->stream));
+            bufs[k] = p0->peer_tiles[k].p;
+            if (stats) stats->kernel_launches += 1;
+        }
+        CK(cudaEventRecord(pd->done, pd->stream));
+    }
+    // ---- assemble on the primary device -----------------------------------------------------------------
+    CK(cudaSetDevice(primary));
+    PerDevice* p0 = pds[0];
+    for (int k = 1; k < n_gpus; ++k) CK(cudaStreamWaitEvent(p0->stream, pds[k]->done, 0));
+    CK(p0->out.reserve(outBytes(&p)));
+    ftb_render_params pa = p;
+    pa.shard_index = 0; pa.shard_count = n_gpus;
+    FrameGeom ga;
+    if ((rc = frameGeom(&pa, ga)) != FTB_OK) return rc;
+    if ((rc = launchAssemble(&pa, ga, bufs.data(), p0->out.p, p0->stream)) != FTB_OK) return rc;
+    if (stats) stats->kernel_launches += 1;
+    CK(cudaMemcpyAsync(out, p0->out.p, outBytes(&p), cudaMemcpyDeviceToHost, p0->stream));
+    if (dbg && dbg->prim_id) {
+        CK(cudaMemcpyAsync(dbg->prim_id, p0->dbg_prim.p, (size_t)full.n_samples * 4, cudaMemcpyDeviceToHost, p0->stream));
+        if (dbg->sub_id) CK(cudaMemcpyAsync(dbg->sub_id, p0->dbg_sub.p, (size_t)full.n_samples * 4, cudaMemcpyDeviceToHost, p0->stream));
+        if (dbg->t) CK(cudaMemcpyAsync(dbg->t, p0->dbg_t.p, (size_t)full.n_samples * 8, cudaMemcpyDeviceToHost, p0->stream));
+    }
+    bool overflow = false;
+    for (int k = 0; k < n_gpus; ++k) {
+        CK(cudaSetDevice(pds[k]->device));
+        if ((rc = finishStats(scene, pds[k], stats, pds[k]->stream, stats != nullptr, &overflow)) != FTB_OK) return rc;
+    }
+    CK(cudaSetDevice(primary));
+    CK(cudaStreamSynchronize(p0->stream));
+    if (stats) stats->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (overflow) return fail(FTB_ERR_HIT_OVERFLOW, "a CSG operand produced more than 32 crossings on one ray");
+    return FTB_OK;
+}
+
+int ftb_shade_rays(ftb_scene* scene, const double* rays_od, int64_t n, const ftb_render_params* params, double* out_rgb,
+                   const ftb_debug_out* dbg, ftb_stats* stats)
+{
+    const auto t0 = std::chrono::steady_clock::now();
+    if (!scene || !params || (n > 0 && (!rays_od || !out_rgb)) || n < 0) return fail(FTB_ERR_BAD_ARG, "null argument");
+    if (params->precision != FTB_PRECISION_FP32 && params->precision != FTB_PRECISION_FP64_VERIFY) return fail(FTB_ERR_BAD_ARG, "bad precision");
+    if (n > (int64_t)FTB_TILE_PIXELS * 0x7fffff00LL / 2) return fail(FTB_ERR_BAD_ARG, "too many rays");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { (void)cudaGetLastError(); return fail(FTB_ERR_NO_DEVICE, "no CUDA device: functracer_b200 has no CPU path"); }
+    if (stats) std::memset(stats, 0, sizeof(*stats));
+    if (n == 0) return FTB_OK;
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    PerDevice* pd = nullptr;
+    int rc = getDevice(scene, dev, &pd);
+    if (rc != FTB_OK) return rc;
+    const bool f64 = params->precision == FTB_PRECISION_FP64_VERIFY;
+    const size_t rs = f64 ? 8 : 4;
+    cudaStream_t s = pd->stream;
+    CK(pd->rays.reserve((size_t)n * 48));
+    CK(cudaMemcpyAsync(pd->rays.p, rays_od, (size_t)n * 48, cudaMemcpyHostToDevice, s));
+    CK(pd->tiles.reserve((size_t)n * 3 * rs));
+    CK(pd->out.reserve((size_t)n * 24));
+    CK(pd->control.reserve(sizeof(Control)));
+    CK(cudaMemsetAsync(pd->control.p, 0, sizeof(Control), s));
+    ftb_debug_out ddbg = {nullptr, nullptr, nullptr};
+    if (dbg && dbg->prim_id) {
+        CK(pd->dbg_prim.reserve((size_t)n * 4)); ddbg.prim_id = static_cast<int32_t*>(pd->dbg_prim.p);
+        if (dbg->sub_id) { CK(pd->dbg_sub.reserve((size_t)n * 4)); ddbg.sub_id = static_cast<int32_t*>(pd->dbg_sub.p); }
+        if (dbg->t) { CK(pd->dbg_t.reserve((size_t)n * 8)); ddbg.t = static_cast<double*>(pd->dbg_t.p); }
+    }
+    Control* ctl = static_cast<Control*>(pd->control.p);
+    const bool wantStats = stats && params->collect_stats;
+    int launches = 0;
+    auto run = [&](auto tag) -> int {
+        typedef decltype(tag) R;
+        SceneStorage<R>& st = storageOf<R>(pd);
+        if (!st.ready) { int r2 = uploadScene<R>(*scene, st); if (r2 != FTB_OK) return r2; }
+        DevFrame<R> F;
+        std::memset(&F, 0, sizeof(F));
+        F.mode = 1; F.spp = 1;
+        F.n_rays = n;
+        F.n_local_tiles = (int)((n + FTB_TILE_PIXELS - 1) / FTB_TILE_PIXELS);
+        F.shard_count = 1;
+        F.rays = static_cast<const double*>(pd->rays.p);
+        F.recursion_limit = params->recursion_limit;
+        F.seed = params->seed;
+        F.out = static_cast<R*>(pd->tiles.p);
+        F.dbg_prim = ddbg.prim_id; F.dbg_sub = ddbg.sub_id; F.dbg_t = ddbg.t;
+        F.tile_counter = &ctl->tile_counter; F.overflow = &ctl->overflow; F.stats = ctl->stats;
+        CK(cudaEventRecord(pd->ev0, s));
+        CK(launch_render<R>(st.view, F, wantStats, pd->sm_count, s, &launches));
+        CK(cudaEventRecord(pd->ev1, s));
+        const long long m = 3 * (long long)n;
+        widen_kernel<R><<<(int)std::min<long long>((m + 255) / 256, 148 * 16), 256, 0, s>>>(static_cast<const R*>(pd->tiles.p), static_cast<double*>(pd->out.p), m);
+        CK(cudaGetLastError());
+        return FTB_OK;
+    };
+    rc = f64 ? run(double()) : run(float());
+    if (rc != FTB_OK) return rc;
+    CK(cudaMemcpyAsync(out_rgb, pd->out.p, (size_t)n * 24, cudaMemcpyDeviceToHost, s));
+    if (ddbg.prim_id) {
+        CK(cudaMemcpyAsync(dbg->prim_id, ddbg.prim_id, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+        if (ddbg.sub_id) CK(cudaMemcpyAsync(dbg->sub_id, ddbg.sub_id, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+        if (ddbg.t) CK(cudaMemcpyAsync(dbg->t, ddbg.t, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
+    }
+    bool overflow = false;
+    if (stats) stats->kernel_launches = launches + 2;
+    if ((rc = finishStats(scene, pd, stats, s, true, &overflow)) != FTB_OK) return rc;
+    if (stats) stats->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (overflow) return fail(FTB_ERR_HIT_OVERFLOW, "a CSG operand produced more than 32 crossings on one ray");
+    return FTB_OK;
+}
+
+}  // extern "C"

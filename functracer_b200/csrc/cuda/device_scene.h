@@ -1,0 +1,109 @@
+// device_scene.h — the structure-of-arrays scene and frame descriptors the kernels consume.
+// Templated on the arithmetic type: float for the product path, double for the FP64
+// verification build.  Filled by api.cu from ftb::Lowered.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ftb {
+
+constexpr int kHitCap = 32;    // per-ray CSG hit stack entries
+constexpr int kMaxLists = 12;  // per-ray CSG list stack depth
+constexpr int kBspStack = 64;  // per-ray BSP traversal stack
+constexpr int kBlockThreads = 128;
+
+template <typename R>
+struct V4;
+template <>
+struct V4<float> {
+    typedef float4 type;
+};
+template <>
+struct V4<double> {
+    typedef double4 type;
+};
+
+enum StatSlot : int {
+    ST_PRIMARY = 0,
+    ST_SHADOW,
+    ST_REFLECTION,
+    ST_SHADED,
+    ST_LEAF0,  // 9 leaf kinds follow (ftb::LeafKind order)
+    ST_XFORM = ST_LEAF0 + 9,
+    ST_BSP_NODES,
+    ST_BOUND_TESTS,
+    ST_CSG_OPS,
+    ST_TRI_TESTS_IN_MESH,
+    ST_COUNT
+};
+
+template <typename R>
+struct DevScene {
+    typedef typename V4<R>::type R4;
+    // leaves
+    const R4* leaf_w2m;     // 3 rows per leaf
+    const int4* leaf_meta;  // x = kind | identity << 8, y = surface, z = prim, w = payload
+    int n_leaves;
+    // top-level items in enumeration order
+    const int4* items;     // x = kind, y = a, z = b, w = casts_shadow
+    const R4* item_bound;  // xyz = centre, w = radius (< 0 unbounded)
+    int n_items;
+    const int2* ops;  // CSG programs: x = kind, y = arg
+    // surfaces
+    const R4* surf_a;    // colour.rgb, roughness
+    const R4* surf_b;    // reflectance, shineyness, 0, 0
+    const int4* surf_i;  // texture, hue, apply_lighting, 0
+    // textures
+    const int4* tex_i;  // op_first, op_count, base_kind, image
+    const R4* tex_c1;
+    const R4* tex_c2;
+    const int* texop_kind;
+    const R* texop_ab;  // 2 per op
+    const uchar4* texels;
+    const int4* img_i;  // x = first texel, y = width, z = height
+    // meshes
+    const int* mesh_root;
+    const R* bsp_aabb;  // 6 per node: min.xyz, max.xyz
+    const int2* bsp_links;   // x = left, y = right (>= 0 branch, < 0 ~leaf)
+    const int2* bsp_leaves;  // x = first triangle, y = count
+    const R4* tris;          // 3 per triangle: v0, e1 = v1 - v0, e2 = v2 - v0
+    // lights
+    const int2* light_i;  // kind, samples
+    const R4* light_a;    // v.xyz (dir or pos), tan(scatter / 2)
+    const R4* light_b;    // falloff c, l, q
+    const R4* light_c;    // colour
+    int n_lights;
+};
+
+template <typename R>
+struct DevFrame {
+    int mode;  // 0 = camera sample grid, 1 = explicit ray list
+    int gw, gh;  // sample grid (W x H, or (W+1) x (H+1) in corner mode)
+    int spp;
+    int tiles_x;
+    int n_local_tiles;  // tiles this shard renders
+    int shard_index, shard_count;
+    long long n_rays;  // mode 1
+    R cam_o[3], cam_k[3], cam_i[3], cam_j[3];
+    R pw, ph, tlx, tly;
+    int has_focus;
+    R focal, tan_half_aperture;
+    const R* jitter;     // 2 * spp
+    const double* rays;  // mode 1: o.xyz d.xyz
+    int recursion_limit;
+    unsigned long long seed;
+    R* out;  // mode 0: tile-major [local tile][256][3]; mode 1: [ray][3]
+    int* dbg_prim;
+    int* dbg_sub;
+    double* dbg_t;
+    unsigned int* tile_counter;
+    unsigned int* overflow;
+    unsigned long long* stats;  // ST_COUNT slots (stats kernels only)
+};
+
+// launchers implemented in render_f32.cu / render_f64.cu
+template <typename R>
+cudaError_t launch_render(const DevScene<R>& s, const DevFrame<R>& f, bool stats, int sm_count, cudaStream_t stream, int* launches);
+
+}  // namespace ftb

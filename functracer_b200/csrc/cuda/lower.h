@@ -1,0 +1,113 @@
+// lower.h — host-side lowering of the reference's SceneGraph (as delivered through
+// ftb_scene_desc) into the flat, leaf-centric form the CUDA kernels consume.
+//
+// What Scene.intersect (FuncTracer/Scene.fs:67-104) does by building closures is done here by
+// building tables:
+//   * every PRIMITIVE instance becomes one or more LEAVES with ONE pre-composed world->model
+//     matrix (the product of the Transform nodes on its path; t is invariant under
+//     Transform.transform, Transform.fs:84-86, so nearest-hit only ever needs this matrix);
+//   * every leaf gets a statically RESOLVED SURFACE: the surface ops on its path
+//     (Ray.fs:47-59) are maps over hits, applied innermost first, so their net effect per leaf
+//     is known before any ray is traced;
+//   * the top-level object list is flattened into ITEMS in the reference's enumeration order
+//     (Ray.group, Ray.fs:34), which is also the tie-break order of Scene.closest;
+//   * each CSG subtree becomes a post-order PROGRAM over a per-ray hit stack (Csg.fs:74-94).
+#pragma once
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../../include/functracer_b200.h"
+
+namespace ftb {
+
+enum LeafKind : int32_t {
+    LEAF_SPHERE = 0,
+    LEAF_PLANE = 1,
+    LEAF_SQUARE = 2,
+    LEAF_CIRCLE = 3,
+    LEAF_CYLINDER = 4,  // open side surface (Cylinder.cylinder)
+    LEAF_CONE = 5,
+    LEAF_CUBE = 6,  // the six squares of Cube.cube fused: sub = face
+    LEAF_TRIANGLE = 7,
+    LEAF_MESH = 8
+};
+
+enum ItemKind : int32_t { ITEM_LEAF = 0, ITEM_CSG = 1 };
+
+enum CsgOpKind : int32_t {
+    OP_LEAF = 0,   // arg = leaf index: push its hit list
+    OP_GROUP = 1,  // arg = n: concatenate the top n lists (Ray.group)
+    OP_EMPTY = 2,  // push an empty list (Group [])
+    OP_UNION = 3,
+    OP_INTERSECT = 4,
+    OP_SUBTRACT = 5,
+    OP_EXCLUDE = 6
+};
+
+struct Leaf {
+    int32_t kind;
+    int32_t surface;
+    int32_t prim;     // depth-first PRIMITIVE-instance index (the debug plane's prim_id)
+    int32_t payload;  // mesh index | triangle index | solidCylinder part (reported as sub_id)
+    int32_t identity; // 1 = w2m is the identity (no transform on the path)
+    int32_t reserved[3];
+    double w2m[12];   // composed world->model, row-major 3x4
+};
+
+struct Surface {
+    int32_t texture;  // -1 = constant colour
+    int32_t hue;      // number of (r,g,b)->(b,r,g) permutations applied after the colour source, mod 3
+    int32_t apply_lighting;
+    int32_t reserved;
+    double colour[3];
+    double roughness, reflectance, shineyness;
+};
+
+struct TexOp {
+    int32_t kind;  // FTB_TEX_SCALE | FTB_TEX_ROTATE
+    int32_t reserved;
+    double a, b;  // scale: (x, y); rotate: (cos, sin)
+};
+
+struct TexDef {
+    int32_t op_first, op_count;  // uv ops in application order (outermost first, Scene.fs:68-74)
+    int32_t base_kind;           // FTB_TEX_GRID | FTB_TEX_IMAGE
+    int32_t image;
+    double c1[3], c2[3];
+};
+
+struct Item {
+    int32_t kind;
+    int32_t a;  // ITEM_LEAF: leaf index; ITEM_CSG: first op
+    int32_t b;  // ITEM_CSG: op count
+    int32_t casts_shadow;  // 0 = every leaf under it has applyLighting = false (Scene.fs:121)
+    // conservative world-space bounding sphere of everything the item can report (radius < 0: unbounded)
+    double bound_c[3];
+    double bound_r;
+};
+
+struct CsgOp {
+    int32_t kind;
+    int32_t arg;
+};
+
+struct Lowered {
+    std::vector<Leaf> leaves;
+    std::vector<Surface> surfaces;
+    std::vector<TexOp> tex_ops;
+    std::vector<TexDef> textures;
+    std::vector<Item> items;
+    std::vector<CsgOp> ops;
+    int32_t n_prims = 0;
+    int32_t max_csg_lists = 0;  // deepest list stack any program needs
+    int32_t max_bsp_depth = 0;
+    bool has_csg = false, has_mesh = false, has_texture = false, has_image = false;
+    bool has_soft_light = false, has_rough = false, has_reflection = false;
+};
+
+// Returns FTB_OK or a negative ftb_status with a message in err.
+int lower_scene(const ftb_scene_desc& d, Lowered& out, std::string& err);
+
+}  // namespace ftb
