@@ -84,6 +84,42 @@ __global__ void widen_kernel(const R* in, double* out, long long n)
 
 }  // namespace ftb
 
+namespace ftb {
+// kernel variants compiled by the Makefile (render_variant.cu), listed through -DFTB_FEAT_LIST_F32 / _F64
+#define X(feat) cudaError_t launch_f32_##feat(const DevScene<float>&, const DevFrame<float>&, bool, int, cudaStream_t, int*);
+FTB_FEAT_LIST_F32
+#undef X
+#define X(feat) cudaError_t launch_f64_##feat(const DevScene<double>&, const DevFrame<double>&, bool, int, cudaStream_t, int*);
+FTB_FEAT_LIST_F64
+#undef X
+static const Variant<float> kVariantsF32[] = {
+#define X(feat) {(unsigned)(feat), (feat) == FT_ALL, launch_f32_##feat},
+    FTB_FEAT_LIST_F32
+#undef X
+};
+static const Variant<double> kVariantsF64[] = {
+#define X(feat) {(unsigned)(feat), (feat) == FT_ALL, launch_f64_##feat},
+    FTB_FEAT_LIST_F64
+#undef X
+};
+template <typename R> struct VariantTable;
+template <> struct VariantTable<float> { static const Variant<float>* begin() { return kVariantsF32; } static int size() { return (int)(sizeof(kVariantsF32) / sizeof(kVariantsF32[0])); } };
+template <> struct VariantTable<double> { static const Variant<double>* begin() { return kVariantsF64; } static int size() { return (int)(sizeof(kVariantsF64) / sizeof(kVariantsF64[0])); } };
+
+// the smallest compiled variant that covers `need` (and has the counting kernel if asked for)
+template <typename R>
+const Variant<R>* pickVariant(unsigned need, bool stats)
+{
+    const Variant<R>* best = nullptr;
+    for (int i = 0; i < VariantTable<R>::size(); ++i) {
+        const Variant<R>* v = VariantTable<R>::begin() + i;
+        if ((v->feat & need) != need || (stats && !v->has_stats)) continue;
+        if (!best || __builtin_popcount(v->feat) < __builtin_popcount(best->feat)) best = v;
+    }
+    return best;
+}
+}  // namespace ftb
+
 namespace {
 
 using namespace ftb;
@@ -210,7 +246,9 @@ int uploadScene(const ftb_scene& sc, SceneStorage<R>& st)
         std::vector<int4> items; std::vector<R4> bounds; std::vector<int2> ops;
         for (const Item& it : L.items) {
             items.push_back(make_int4(it.kind, it.a, it.b, it.casts_shadow));
-            bounds.push_back(Mk4<R>::make(it.bound_c[0], it.bound_c[1], it.bound_c[2], it.bound_r));
+            // conservative: radius inflated by 0.2 % + 1e-5 so that FP32 rounding of the test cannot cull a true hit
+            const double ri = it.bound_r < 0 ? -1.0 : it.bound_r * 1.002 + 1e-5;
+            bounds.push_back(Mk4<R>::make(it.bound_c[0], it.bound_c[1], it.bound_c[2], ri < 0 ? -1.0 : ri * ri));
         }
         for (const CsgOp& op : L.ops) ops.push_back(make_int2(op.kind, op.arg));
         UP(items, v.items) UP(bounds, v.item_bound) UP(ops, v.ops)
@@ -420,7 +458,9 @@ int launchFrame(ftb_scene* sc, PerDevice* pd, const ftb_camera* cam, const ftb_r
     const bool wantStats = stats && p->collect_stats;
     if (timeKernel) CK(cudaEventRecord(pd->ev0, stream));
     int launches = 0;
-    CK(launch_render<R>(st.view, F, wantStats, pd->sm_count, stream, &launches));
+    const Variant<R>* var = pickVariant<R>(sc->L.features | (cam->has_focus ? (unsigned)FT_RNG : 0u), wantStats);
+    if (!var) return fail(FTB_ERR_UNSUPPORTED, "no kernel variant covers this scene's feature mask");
+    CK(var->launch(st.view, F, wantStats, pd->sm_count, stream, &launches));
     if (timeKernel) CK(cudaEventRecord(pd->ev1, stream));
     if (stats) stats->kernel_launches += launches + 1;  // + the control-block memset
     return FTB_OK;
@@ -734,7 +774,9 @@ int ftb_shade_rays(ftb_scene* scene, const double* rays_od, int64_t n, const ftb
         F.dbg_prim = ddbg.prim_id; F.dbg_sub = ddbg.sub_id; F.dbg_t = ddbg.t;
         F.tile_counter = &ctl->tile_counter; F.overflow = &ctl->overflow; F.stats = ctl->stats;
         CK(cudaEventRecord(pd->ev0, s));
-        CK(launch_render<R>(st.view, F, wantStats, pd->sm_count, s, &launches));
+        const Variant<R>* var = pickVariant<R>(scene->L.features, wantStats);
+        if (!var) return fail(FTB_ERR_UNSUPPORTED, "no kernel variant covers this scene's feature mask");
+        CK(var->launch(st.view, F, wantStats, pd->sm_count, s, &launches));
         CK(cudaEventRecord(pd->ev1, s));
         const long long m = 3 * (long long)n;
         widen_kernel<R><<<(int)std::min<long long>((m + 255) / 256, 148 * 16), 256, 0, s>>>(static_cast<const R*>(pd->tiles.p), static_cast<double*>(pd->out.p), m);

@@ -24,6 +24,19 @@ struct V4<double> {
     typedef double4 type;
 };
 
+// Kernel feature mask: which primitive classes / shading terms a kernel variant contains.  A scene is
+// rendered by the smallest compiled variant whose mask covers lower.h's Lowered::features.
+enum Feature : unsigned {
+    FT_CUBE = 0x01,   // LEAF_CUBE
+    FT_ROUND = 0x02,  // LEAF_SQUARE, LEAF_CIRCLE, LEAF_CYLINDER, LEAF_CONE
+    FT_MESH = 0x04,   // LEAF_TRIANGLE, LEAF_MESH (BSP traversal)
+    FT_CSG = 0x08,    // CSG programs
+    FT_TEX = 0x10,    // grid / image textures, sphere uv
+    FT_ROUGH = 0x20,  // Oren-Nayar diffuse
+    FT_RNG = 0x40,    // soft directional lights, depth of field
+    FT_ALL = 0x7f
+};
+
 enum StatSlot : int {
     ST_PRIMARY = 0,
     ST_SHADOW,
@@ -47,7 +60,7 @@ struct DevScene {
     int n_leaves;
     // top-level items in enumeration order
     const int4* items;     // x = kind, y = a, z = b, w = casts_shadow
-    const R4* item_bound;  // xyz = centre, w = radius (< 0 unbounded)
+    const R4* item_bound;  // xyz = centre, w = (inflated radius)^2 of a conservative bounding sphere (< 0 unbounded)
     int n_items;
     const int2* ops;  // CSG programs: x = kind, y = arg
     // surfaces
@@ -102,8 +115,12 @@ struct DevFrame {
     unsigned long long* stats;  // ST_COUNT slots (stats kernels only)
 };
 
-// launchers implemented in render_f32.cu / render_f64.cu
+// A compiled kernel variant (render_variant.cu, one translation unit per FEAT mask / precision).
 template <typename R>
-cudaError_t launch_render(const DevScene<R>& s, const DevFrame<R>& f, bool stats, int sm_count, cudaStream_t stream, int* launches);
+struct Variant {
+    unsigned feat;
+    bool has_stats;  // the counting kernel is only compiled into the FT_ALL variants
+    cudaError_t (*launch)(const DevScene<R>& s, const DevFrame<R>& f, bool stats, int sm_count, cudaStream_t stream, int* launches);
+};
 
 }  // namespace ftb

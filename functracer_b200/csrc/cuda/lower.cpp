@@ -451,7 +451,19 @@ int lower_scene(const ftb_scene_desc& d, Lowered& out, std::string& err)
     Ctx cx;
     cx.w2m = kIdentity;
     lw.walk(d.root, cx, 0);
-    return lw.status;
+    if (lw.status != FTB_OK) return lw.status;
+    unsigned f = 0;
+    for (const Leaf& lf : out.leaves) {
+        if (lf.kind == LEAF_CUBE) f |= 0x01;
+        if (lf.kind == LEAF_SQUARE || lf.kind == LEAF_CIRCLE || lf.kind == LEAF_CYLINDER || lf.kind == LEAF_CONE) f |= 0x02;
+        if (lf.kind == LEAF_TRIANGLE || lf.kind == LEAF_MESH) f |= 0x04;
+    }
+    if (out.has_csg) f |= 0x08;
+    if (out.has_texture) f |= 0x10;
+    if (out.has_rough) f |= 0x20;
+    if (out.has_soft_light) f |= 0x40;
+    out.features = f;
+    return FTB_OK;
 }
 
 }  // namespace ftb

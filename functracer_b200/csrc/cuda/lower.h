@@ -105,6 +105,9 @@ struct Lowered {
     int32_t max_bsp_depth = 0;
     bool has_csg = false, has_mesh = false, has_texture = false, has_image = false;
     bool has_soft_light = false, has_rough = false, has_reflection = false;
+    // Kernel features this scene needs, as device_scene.h `Feature` bits (cube 1, round 2, mesh 4, csg 8,
+    // texture 16, Oren-Nayar 32, rng 64); camera depth of field adds rng at render time.
+    unsigned features = 0;
 };
 
 // Returns FTB_OK or a negative ftb_status with a message in err.

@@ -2,19 +2,24 @@
 // FuncTracer/Shading.fs:131-147) as ONE persistent CUDA kernel for sm_100a.
 //
 // Execution model (DESIGN.md "kernel"):
-//   * one CTA set per SM, every warp autonomous; no block-level barrier anywhere in the loop;
-//   * work = 16x16-pixel tiles handed out by a per-GPU atomic tile counter; inside a warp the
-//     pixels of the current tile are dealt to lanes with ballot + popc (a warp-level scan), so a
-//     lane whose path ended is immediately re-armed with the next sample / pixel instead of
-//     idling ("compaction by regeneration": the 32 lanes stay full until the frame runs out);
-//   * F#'s recursion (getColourForRay, Shading.fs:131-139) is an iterative, depth-bounded loop
-//     per lane: the reflection ray and its running weight live in registers, so the bounce
-//     "queue" costs zero bytes of HBM traffic; shadow rays are traced inline;
-//   * a lane owns a pixel for all of its samples, so the per-pixel blend happens in sample
-//     order exactly like Array.average (Image.fs:112-116) with no atomics.
-//   * the whole scene is brute-forced per ray in the reference's enumeration order (there is no
-//     object-level index in the reference, Ray.fs:34): all lanes of a warp read the same leaf
-//     record at the same time (one broadcast transaction), and tie-breaks fall out of the order.
+//   * persistent grid (a multiple of the SM count), every warp autonomous, no block barrier;
+//   * work = 8x4-pixel blocks handed out by a per-GPU atomic queue; the pixels of a block are
+//     dealt to lanes with ballot + popc (a warp-level scan), and a lane whose path ended is
+//     re-armed at once with its next sample / pixel ("compaction by regeneration");
+//   * every lane is a small state machine whose only expensive step is "trace my current ray":
+//     the ray may be a primary / reflection ray (nearest hit) or a shadow ray (any hit).  One
+//     loop iteration = one traced ray per lane, so the scene-intersection code exists ONCE in
+//     the kernel (instruction-cache footprint) and lanes that missed do not wait for lanes that
+//     shade.  F#'s recursion (getColourForRay, Shading.fs:131-139) becomes this iterative,
+//     depth-bounded loop; the bounce "queue" is the lane's registers: zero HBM traffic;
+//   * a lane owns a pixel for all of its samples: the blend happens in sample order exactly
+//     like Array.average (Image.fs:112-116), no atomics;
+//   * items (top-level objects) are visited in the reference's enumeration order (Ray.fs:34) so
+//     ties break as Scene.closest does; a conservative bounding-sphere test per item skips
+//     objects the ray's line cannot touch (the reference has no such index; it cannot change a
+//     result because a culled item has no crossing at all on the line);
+//   * the kernel is compiled in several feature-specialised variants (FEAT mask) so that a scene
+//     only pays instruction-cache space for the primitive classes and shading terms it uses.
 //
 // Templated on R: float = product, double = FP64 verification build (compiled --fmad=false).
 #pragma once
@@ -173,6 +178,39 @@ FTB_DEV bool quadratic(R a, R b, R c, R& t0, R& t1)
     return true;
 }
 
+// Roots of the canonical quadrics  x^2 + wy y^2 + z^2 = k  along o + t d  (sphere wy = 1, k = 1, Sphere.fs:11-15;
+// cylinder wy = 0, k = 1, Cylinder.fs:9-13; cone about its apex wy = -1, k = 0, Cone.fs:9-15), far root first
+// like Math.quadratic.
+//   double (verification build): the reference's literal a, b, c and Math.quadratic, operation for operation.
+//   float (product build): the same roots from a re-centred origin.  With o far from the surface (the moon
+//   scene's camera is 50 model units from a unit sphere) b^2 and 4ac agree in their leading digits and FP32
+//   loses the discriminant (error ~ 1e-4 in t: more than the 1e-4 shadow-ray offset of Shading.fs:111, i.e.
+//   shadow acne).  Sliding the origin to the point of closest approach to the model origin, o' = o + ts d,
+//   makes |o'| ~ the object's size and b ~ 0; t = t' + ts.  Same real-arithmetic roots, FP32-safe rounding.
+template <int KIND, typename R>  // KIND: 0 sphere, 1 cylinder, 2 cone (o already relative to the apex)
+FTB_DEV bool quadricRoots(Vec<R> o, Vec<R> d, R& t0, R& t1)
+{
+    if constexpr (sizeof(R) == 8) {
+        R a, b, c;
+        if (KIND == 0) { a = dot(d, d); b = R(2) * dot(o, d); c = dot(o, o) - R(1); }
+        else if (KIND == 1) { a = d.x * d.x + d.z * d.z; b = R(2) * (o.x * d.x + o.z * d.z); c = o.x * o.x + o.z * o.z - R(1); }
+        else { a = d.x * d.x + d.z * d.z - d.y * d.y; b = R(2) * (o.x * d.x + o.z * d.z - o.y * d.y); c = o.x * o.x + o.z * o.z - o.y * o.y; }
+        return quadratic(a, b, c, t0, t1);
+    } else {
+        const R wy = KIND == 0 ? R(1) : (KIND == 1 ? R(0) : R(-1));
+        const R k = KIND == 2 ? R(0) : R(1);
+        const R dd = dot(d, d);
+        const R ts = dd > R(0) ? -dot(o, d) / dd : R(0);
+        const Vec<R> oc = mk<R>(fmaf(ts, d.x, o.x), fmaf(ts, d.y, o.y), fmaf(ts, d.z, o.z));
+        const R a = d.x * d.x + d.z * d.z + wy * d.y * d.y;
+        const R b = R(2) * (oc.x * d.x + oc.z * d.z + wy * oc.y * d.y);
+        const R c = (oc.x * oc.x + oc.z * oc.z + wy * oc.y * oc.y) - k;
+        if (!quadratic(a, b, c, t0, t1)) return false;
+        t0 += ts; t1 += ts;
+        return true;
+    }
+}
+
 // Plane.intersect for Plane(Zero, unitY) in the leaf's frame (Plane.fs:9-20).  Returns false if no hit.
 template <typename R>
 FTB_DEV bool planeT(const Ray<R>& r, R& t, Vec<R>& p)
@@ -232,9 +270,10 @@ FTB_DEV bool triangleT(const DevScene<R>& S, int tri, const Ray<R>& ray, R& t)
     return t > epsilon;
 }
 
+
 // ---- leaf intersection: calls sink.hit(t, sub) for every crossing, in the reference's order ---------
 // sub: cube face 0..5 (Cube.fs:24), triangle index for meshes, else the leaf's payload.
-template <typename R, bool STATS, class Sink>
+template <typename R, unsigned FEAT, bool STATS, class Sink>
 FTB_DEV void intersectLeaf(const DevScene<R>& S, int leaf, const Ray<R>& wr, Sink& sink, Counters<STATS>& cn)
 {
     const int4 meta = __ldg(S.leaf_meta + leaf);
@@ -243,130 +282,128 @@ FTB_DEV void intersectLeaf(const DevScene<R>& S, int leaf, const Ray<R>& wr, Sin
     const Ray<R> r = toModel(S, leaf, identity, wr);
     cn.add(ST_LEAF0 + kind);
     if (!identity) cn.add(ST_XFORM);
-    switch (kind) {
-    case LEAF_SPHERE: {  // Sphere.fs:11-21
-        R a = dot(r.d, r.d), b = R(2) * dot(r.o, r.d), c = dot(r.o, r.o) - R(1), t0, t1;
-        if (quadratic(a, b, c, t0, t1)) { sink.hit(t0, meta.w); sink.hit(t1, meta.w); }
-        break;
+    if (kind == LEAF_SPHERE) {  // Sphere.fs:11-21
+        R t0, t1;
+        if (quadricRoots<0>(r.o, r.d, t0, t1)) { sink.hit(t0, meta.w); sink.hit(t1, meta.w); }
+        return;
     }
-    case LEAF_PLANE: {  // Plane.fs:32-33
+    if (kind == LEAF_PLANE) {  // Plane.fs:32-33
         R t; Vec<R> p;
         if (planeT(r, t, p)) sink.hit(t, meta.w);
-        break;
+        return;
     }
-    case LEAF_SQUARE: {  // Cube.fs:9-15
-        R t; Vec<R> p;
-        if (planeT(r, t, p) && (p.x >= R(0)) && (p.x <= R(1)) && (p.z >= R(0)) && (p.z <= R(1))) sink.hit(t, meta.w);
-        break;
-    }
-    case LEAF_CIRCLE: {  // Cylinder.fs:22
-        R t; Vec<R> p;
-        if (planeT(r, t, p) && length(p) < R(1)) sink.hit(t, meta.w);
-        break;
-    }
-    case LEAF_CYLINDER: {  // Cylinder.fs:8-20
-        R a = r.d.x * r.d.x + r.d.z * r.d.z, b = R(2) * (r.o.x * r.d.x + r.o.z * r.d.z), c = r.o.x * r.o.x + r.o.z * r.o.z - R(1), t0, t1;
-        if (quadratic(a, b, c, t0, t1)) {
-            R py = r.o.y + t0 * r.d.y;
-            if (py >= R(0) && py <= R(1)) sink.hit(t0, meta.w);
-            py = r.o.y + t1 * r.d.y;
-            if (py >= R(0) && py <= R(1)) sink.hit(t1, meta.w);
-        }
-        break;
-    }
-    case LEAF_CONE: {  // Cone.fs:7-28
-        R oy = r.o.y - R(1);
-        R a = r.d.x * r.d.x + r.d.z * r.d.z - r.d.y * r.d.y, b = R(2) * (r.o.x * r.d.x + r.o.z * r.d.z - oy * r.d.y),
-          c = r.o.x * r.o.x + r.o.z * r.o.z - oy * oy, t0, t1;
-        if (quadratic(a, b, c, t0, t1)) {
-            R py = (oy + t0 * r.d.y) + R(1);
-            if (py >= R(0) && py <= R(1)) sink.hit(t0, meta.w);
-            py = (oy + t1 * r.d.y) + R(1);
-            if (py >= R(0) && py <= R(1)) sink.hit(t1, meta.w);
-        }
-        break;
-    }
-    case LEAF_CUBE: {  // Cube.fs:17-25, the six squares in the cube's centred frame shifted by +.5
-        const R eps = R(0.0000001);
-        const R ox = r.o.x + R(0.5), oy = r.o.y + R(0.5), oz = r.o.z + R(0.5);
-        // face f: plane coordinate w (origin wo, direction wd), offset k in {0,1}, in-face coords (a, b)
-        // bottom/top: w = y, (a,b) = (x,z); left/right: w = x, (a,b) = (y,z); front/back: w = z, (a,b) = (x,y).
-        // num/denom signs follow each square's own frame (DESIGN.md "cube"): bottom/top: num = k - w, denom = +wd;
-        // left/right/front/back (rotated frames): num = w - k, denom = -wd.
+    if constexpr ((FEAT & FT_CUBE) != 0) {
+        if (kind == LEAF_CUBE) {  // Cube.fs:17-25, the six squares in the cube's centred frame shifted by +.5
+            const R eps = R(0.0000001);
+            const R ox = r.o.x + R(0.5), oy = r.o.y + R(0.5), oz = r.o.z + R(0.5);
+            // face f: plane coordinate w (origin wo, direction wd), offset k in {0,1}, in-face coords (a, b)
+            // bottom/top: w = y, (a,b) = (x,z); left/right: w = x, (a,b) = (y,z); front/back: w = z, (a,b) = (x,y).
+            // num/denom signs follow each square's own frame (DESIGN.md "cube"): bottom/top: num = k - w, denom = +wd;
+            // left/right/front/back (rotated frames): num = w - k, denom = -wd.
 #define FTB_CUBE_FACE(face, wo, wd, ao, ad, bo, bd, k, rotated)                                   \
-        {                                                                                         \
-            R num = (rotated) ? ((wo) - R(k)) : (R(k) - (wo));                                    \
-            R denom = (rotated) ? -(wd) : (wd);                                                   \
-            R t; bool ok = true;                                                                  \
-            if (abs_(denom) < eps) { if (num < eps) t = R(0); else ok = false; }                  \
-            else t = num / denom;                                                                 \
-            if (ok) {                                                                             \
-                R pa = (ao) + t * (ad), pb = (bo) + t * (bd);                                     \
-                if ((pa >= R(0)) && (pa <= R(1)) && (pb >= R(0)) && (pb <= R(1))) sink.hit(t, face); \
-            }                                                                                     \
-        }
-        FTB_CUBE_FACE(0, oy, r.d.y, ox, r.d.x, oz, r.d.z, 0, false)
-        FTB_CUBE_FACE(1, oy, r.d.y, ox, r.d.x, oz, r.d.z, 1, false)
-        FTB_CUBE_FACE(2, ox, r.d.x, oy, r.d.y, oz, r.d.z, 0, true)
-        FTB_CUBE_FACE(3, ox, r.d.x, oy, r.d.y, oz, r.d.z, 1, true)
-        FTB_CUBE_FACE(4, oz, r.d.z, ox, r.d.x, oy, r.d.y, 0, true)
-        FTB_CUBE_FACE(5, oz, r.d.z, ox, r.d.x, oy, r.d.y, 1, true)
+            {                                                                                         \
+                R num = (rotated) ? ((wo) - R(k)) : (R(k) - (wo));                                    \
+                R denom = (rotated) ? -(wd) : (wd);                                                   \
+                R t; bool ok = true;                                                                  \
+                if (abs_(denom) < eps) { if (num < eps) t = R(0); else ok = false; }                  \
+                else t = num / denom;                                                                 \
+                if (ok) {                                                                             \
+                    R pa = (ao) + t * (ad), pb = (bo) + t * (bd);                                     \
+                    if ((pa >= R(0)) && (pa <= R(1)) && (pb >= R(0)) && (pb <= R(1))) sink.hit(t, face); \
+                }                                                                                     \
+            }
+            FTB_CUBE_FACE(0, oy, r.d.y, ox, r.d.x, oz, r.d.z, 0, false)
+            FTB_CUBE_FACE(1, oy, r.d.y, ox, r.d.x, oz, r.d.z, 1, false)
+            FTB_CUBE_FACE(2, ox, r.d.x, oy, r.d.y, oz, r.d.z, 0, true)
+            FTB_CUBE_FACE(3, ox, r.d.x, oy, r.d.y, oz, r.d.z, 1, true)
+            FTB_CUBE_FACE(4, oz, r.d.z, ox, r.d.x, oy, r.d.y, 0, true)
+            FTB_CUBE_FACE(5, oz, r.d.z, ox, r.d.x, oy, r.d.y, 1, true)
 #undef FTB_CUBE_FACE
-        break;
+            return;
+        }
     }
-    case LEAF_TRIANGLE: {
-        R t;
-        if (triangleT(S, meta.w, r, t)) sink.hit(t, 0);
-        break;
+    if constexpr ((FEAT & FT_ROUND) != 0) {
+        if (kind == LEAF_SQUARE) {  // Cube.fs:9-15
+            R t; Vec<R> p;
+            if (planeT(r, t, p) && (p.x >= R(0)) && (p.x <= R(1)) && (p.z >= R(0)) && (p.z <= R(1))) sink.hit(t, meta.w);
+            return;
+        }
+        if (kind == LEAF_CIRCLE) {  // Cylinder.fs:22
+            R t; Vec<R> p;
+            if (planeT(r, t, p) && length(p) < R(1)) sink.hit(t, meta.w);
+            return;
+        }
+        if (kind == LEAF_CYLINDER) {  // Cylinder.fs:8-20
+            R t0, t1;
+            if (quadricRoots<1>(r.o, r.d, t0, t1)) {
+                R py = r.o.y + t0 * r.d.y;
+                if (py >= R(0) && py <= R(1)) sink.hit(t0, meta.w);
+                py = r.o.y + t1 * r.d.y;
+                if (py >= R(0) && py <= R(1)) sink.hit(t1, meta.w);
+            }
+            return;
+        }
+        if (kind == LEAF_CONE) {  // Cone.fs:7-28
+            R oy = r.o.y - R(1);
+            R t0, t1;
+            if (quadricRoots<2>(mk<R>(r.o.x, oy, r.o.z), r.d, t0, t1)) {
+                R py = (oy + t0 * r.d.y) + R(1);
+                if (py >= R(0) && py <= R(1)) sink.hit(t0, meta.w);
+                py = (oy + t1 * r.d.y) + R(1);
+                if (py >= R(0) && py <= R(1)) sink.hit(t1, meta.w);
+            }
+            return;
+        }
     }
-    case LEAF_MESH: {  // BspMesh.intersect (BspMesh.fs:67-76): AABB gate, right subtree, then left
-        int stack[kBspStack];
-        int sp = 0;
-        stack[sp++] = __ldg(S.mesh_root + meta.w);
-        const Vec<R> inv = mk<R>(R(1) / r.d.x, R(1) / r.d.y, R(1) / r.d.z);
-        while (sp > 0) {
-            int link = stack[--sp];
-            if (link < 0) {
-                const int2 lf = __ldg(S.bsp_leaves + (~link));
-                for (int i = 0; i < lf.y; ++i) {
-                    R t;
-                    cn.add(ST_TRI_TESTS_IN_MESH);
-                    if (triangleT(S, lf.x + i, r, t)) sink.hit(t, lf.x + i);
-                    if (sink.done()) { sp = 0; break; }
-                }
-            } else {
-                cn.add(ST_BSP_NODES);
-                if (aabbIntersects(S.bsp_aabb + 6 * link, r, inv)) {
-                    const int2 ln = __ldg(S.bsp_links + link);
-                    if (sp + 2 <= kBspStack) { stack[sp++] = ln.x; stack[sp++] = ln.y; }  // right pops first
+    if constexpr ((FEAT & FT_MESH) != 0) {
+        if (kind == LEAF_TRIANGLE) {
+            R t;
+            if (triangleT(S, meta.w, r, t)) sink.hit(t, 0);
+            return;
+        }
+        if (kind == LEAF_MESH) {  // BspMesh.intersect (BspMesh.fs:67-76): AABB gate, right subtree, then left
+            int stack[kBspStack];
+            int sp = 0;
+            stack[sp++] = __ldg(S.mesh_root + meta.w);
+            const Vec<R> inv = mk<R>(R(1) / r.d.x, R(1) / r.d.y, R(1) / r.d.z);
+            while (sp > 0) {
+                int link = stack[--sp];
+                if (link < 0) {
+                    const int2 lf = __ldg(S.bsp_leaves + (~link));
+                    for (int i = 0; i < lf.y; ++i) {
+                        R t;
+                        cn.add(ST_TRI_TESTS_IN_MESH);
+                        if (triangleT(S, lf.x + i, r, t)) sink.hit(t, lf.x + i);
+                        if (sink.done()) { sp = 0; break; }
+                    }
+                } else {
+                    cn.add(ST_BSP_NODES);
+                    if (aabbIntersects(S.bsp_aabb + 6 * link, r, inv)) {
+                        const int2 ln = __ldg(S.bsp_links + link);
+                        if (sp + 2 <= kBspStack) { stack[sp++] = ln.x; stack[sp++] = ln.y; }  // right pops first
+                    }
                 }
             }
+            return;
         }
-        break;
-    }
     }
 }
 
 // ---- sinks ----------------------------------------------------------------------------------------------
-// Scene.closest (Scene.fs:112-116): smallest t >= 0, first in enumeration order on ties.
+// Scene.closest (Scene.fs:112-116): smallest t >= 0, first in enumeration order on ties — and, with
+// `limit` preset to maxDistance and `any` set, Scene.lightIsBocked (Scene.fs:119-121) for leaves whose
+// surface has applyLighting = true: any hit with 0 <= t < maxDistance.
 template <typename R>
-struct NearestSink {
-    R t;
+struct RaySink {
+    R limit;
     int leaf, sub, flip;
     int cur;  // leaf being intersected
+    bool any;
     FTB_DEV void hit(R ht, int hsub)
     {
-        if (ht >= R(0) && ht < t) { t = ht; leaf = cur; sub = hsub; flip = 0; }
+        if (ht >= R(0) && ht < limit) { limit = ht; leaf = cur; sub = hsub; flip = 0; }
     }
-    FTB_DEV bool done() const { return false; }
-};
-// Scene.lightIsBocked (Scene.fs:119-121) for a leaf whose surface has applyLighting = true.
-template <typename R>
-struct AnySink {
-    R maxDistance;
-    bool blocked;
-    FTB_DEV void hit(R ht, int) { if (ht >= R(0) && ht < maxDistance) blocked = true; }
-    FTB_DEV bool done() const { return blocked; }
+    FTB_DEV bool done() const { return any && leaf >= 0; }
 };
 // CSG operand: append to the per-ray hit stack.
 template <typename R>
@@ -406,7 +443,7 @@ FTB_DEV unsigned csgRuleTable(int op)
 
 // Evaluates one CSG program (Csg.constructedSolid, Csg.fs:74-94) on the per-ray hit stack.
 // On return stack[0..n) holds the root's crossings sorted by t.
-template <typename R, bool STATS>
+template <typename R, unsigned FEAT, bool STATS>
 FTB_DEV int evalCsg(const DevScene<R>& S, int opFirst, int opCount, const Ray<R>& wr, HitRec<R>* stack, bool& overflow, Counters<STATS>& cn)
 {
     int counts[kMaxLists];
@@ -418,7 +455,7 @@ FTB_DEV int evalCsg(const DevScene<R>& S, int opFirst, int opCount, const Ray<R>
         if (op.x == OP_LEAF) {
             int start = sink.top;
             sink.cur = op.y;
-            intersectLeaf<R, STATS>(S, op.y, wr, sink, cn);
+            intersectLeaf<R, FEAT & ~FT_MESH, STATS>(S, op.y, wr, sink, cn);  // meshes are rejected as CSG operands at lowering
             if (nlists < kMaxLists) counts[nlists++] = sink.top - start; else sink.overflow = true;
         } else if (op.x == OP_GROUP) {
             int c = 0;
@@ -466,63 +503,56 @@ struct HitInfo {
     int leaf, sub, flip;
 };
 
-// closest over the whole scene: Scene.intersectScene (Scene.fs:118)
-template <typename R, bool STATS>
-FTB_DEV HitInfo<R> traceNearest(const DevScene<R>& S, const Ray<R>& wr, bool& overflow, Counters<STATS>& cn)
+// One ray against the whole scene.
+//   any = false: Scene.intersectScene = geometry >> closest (Scene.fs:112-118); limit = +inf.
+//   any = true : Scene.lightIsBocked (Scene.fs:119-121); limit = maxDistance; leaf >= 0 means blocked.
+template <typename R, unsigned FEAT, bool STATS>
+FTB_DEV HitInfo<R> traceScene(const DevScene<R>& S, const Ray<R>& wr, R limit, bool any, bool& overflow, Counters<STATS>& cn)
 {
-    NearestSink<R> best;
-    best.t = inf_<R>(); best.leaf = -1; best.sub = 0; best.flip = 0;
+    typedef typename V4<R>::type R4;
+    RaySink<R> best;
+    best.limit = limit; best.leaf = -1; best.sub = 0; best.flip = 0; best.any = any; best.cur = 0;
+    const R inv_dd = R(1) / dot(wr.d, wr.d);
     for (int it = 0; it < S.n_items; ++it) {
+        if (any && best.leaf >= 0) break;
         const int4 item = __ldg(S.items + it);
+        if (any && !item.w) continue;  // nothing under it has applyLighting
+        const R4 bound = ldg4<R>(S.item_bound + it);  // xyz = centre, w = inflated radius^2 (< 0: unbounded)
+        if (bound.w >= R(0)) {
+            cn.add(ST_BOUND_TESTS);
+            const Vec<R> oc = mk<R>(bound.x - wr.o.x, bound.y - wr.o.y, bound.z - wr.o.z);
+            const R b = dot(oc, wr.d);
+            const R tc = b * inv_dd;
+            const Vec<R> l = mk<R>(oc.x - tc * wr.d.x, oc.y - tc * wr.d.y, oc.z - tc * wr.d.z);  // centre -> line, perpendicular
+            const R oc2 = dot(oc, oc);
+            if (dot(l, l) > bound.w + R(1e-6) * oc2) continue;  // the ray's line misses the bound: no crossing at all
+            if (b < R(0) && oc2 > bound.w) continue;           // bound entirely behind the origin: every crossing has t < 0
+        }
         if (item.x == ITEM_LEAF) {
             best.cur = item.y;
-            intersectLeaf<R, STATS>(S, item.y, wr, best, cn);
-        } else {
+            intersectLeaf<R, FEAT, STATS>(S, item.y, wr, best, cn);
+        } else if constexpr ((FEAT & FT_CSG) != 0) {
             HitRec<R> stack[kHitCap];
-            const int n = evalCsg<R, STATS>(S, item.y, item.z, wr, stack, overflow, cn);
-            for (int k = 0; k < n; ++k) {  // sorted by t: the first t >= 0 that beats best wins
+            const int n = evalCsg<R, FEAT, STATS>(S, item.y, item.z, wr, stack, overflow, cn);
+            for (int k = 0; k < n; ++k) {  // sorted by t
                 const R ht = stack[k].t;
-                if (ht >= R(0)) {
-                    if (ht < best.t) {
-                        best.t = ht; best.leaf = (int)(stack[k].id & kIdLeafMask); best.sub = (int)((stack[k].id >> kIdSubShift) & 7u);
+                if (!(ht >= R(0))) continue;
+                if (!any) {  // the first t >= 0 is this item's candidate; it wins if it beats best
+                    if (ht < best.limit) {
+                        best.limit = ht; best.leaf = (int)(stack[k].id & kIdLeafMask); best.sub = (int)((stack[k].id >> kIdSubShift) & 7u);
                         best.flip = (stack[k].id & kIdFlip) ? 1 : 0;
                     }
                     break;
                 }
+                if (!(ht < best.limit)) break;
+                const int leaf = (int)(stack[k].id & kIdLeafMask);
+                if (__ldg(S.surf_i + __ldg(S.leaf_meta + leaf).y).z) { best.leaf = leaf; break; }
             }
         }
     }
     HitInfo<R> h;
-    h.t = best.t; h.leaf = best.leaf; h.sub = best.sub; h.flip = best.flip;
+    h.t = best.limit; h.leaf = best.leaf; h.sub = best.sub; h.flip = best.flip;
     return h;
-}
-
-// lightIsBocked over the whole scene (Scene.fs:119-121)
-template <typename R, bool STATS>
-FTB_DEV bool traceAny(const DevScene<R>& S, const Ray<R>& wr, R maxDistance, bool& overflow, Counters<STATS>& cn)
-{
-    cn.add(ST_SHADOW);
-    AnySink<R> any;
-    any.maxDistance = maxDistance; any.blocked = false;
-    for (int it = 0; it < S.n_items && !any.blocked; ++it) {
-        const int4 item = __ldg(S.items + it);
-        if (!item.w) continue;  // nothing under it has applyLighting
-        if (item.x == ITEM_LEAF) {
-            intersectLeaf<R, STATS>(S, item.y, wr, any, cn);
-        } else {
-            HitRec<R> stack[kHitCap];
-            const int n = evalCsg<R, STATS>(S, item.y, item.z, wr, stack, overflow, cn);
-            for (int k = 0; k < n; ++k) {
-                const R ht = stack[k].t;
-                if (ht >= R(0) && ht < maxDistance) {
-                    const int leaf = (int)(stack[k].id & kIdLeafMask);
-                    const int surf = __ldg(S.leaf_meta + leaf).y;
-                    if (__ldg(S.surf_i + surf).z) { any.blocked = true; break; }
-                }
-            }
-        }
-    }
-    return any.blocked;
 }
 
 // ---- textures (Textures/Texture.fs, Textures/Image.fs:27-36) ---------------------------------------------
@@ -588,7 +618,7 @@ struct Fragment {
     bool applyLighting;
 };
 
-template <typename R>
+template <typename R, unsigned FEAT>
 FTB_DEV Fragment<R> finalise(const DevScene<R>& S, const Ray<R>& wr, const HitInfo<R>& h)
 {
     typedef typename V4<R>::type R4;
@@ -599,48 +629,33 @@ FTB_DEV Fragment<R> finalise(const DevScene<R>& S, const Ray<R>& wr, const HitIn
     const Vec<R> pm = mk<R>(r.o.x + h.t * r.d.x, r.o.y + h.t * r.d.y, r.o.z + h.t * r.d.z);
     Vec<R> nm = mk<R>(R(0), R(1), R(0));
     R u = R(0), v = R(0);
-    switch (kind) {
-    case LEAF_SPHERE:
+    if (kind == LEAF_SPHERE) {
         nm = normalise(pm);
-        break;
-    case LEAF_PLANE: case LEAF_SQUARE: case LEAF_CIRCLE:
+    } else if (kind == LEAF_PLANE || kind == LEAF_SQUARE || kind == LEAF_CIRCLE) {
         u = pm.x; v = pm.z;
-        break;
-    case LEAF_CYLINDER: {
-        Vec<R> n = normalise(mk<R>(pm.x, R(0), pm.z));
-        nm = (dot(n, r.d) < R(0)) ? n : -n;
-        break;
-    }
-    case LEAF_CONE: {
-        Vec<R> n = normalise(mk<R>(pm.x, -(pm.y - R(1)), pm.z));
-        nm = (dot(n, r.d) < R(0)) ? n : -n;
-        break;
-    }
-    case LEAF_CUBE: {
-        const R x1 = pm.x + R(0.5), y1 = pm.y + R(0.5), z1 = pm.z + R(0.5);
-        switch (h.sub) {
-        case 0: nm = mk<R>(R(0), R(-1), R(0)); u = x1; v = z1; break;
-        case 1: nm = mk<R>(R(0), R(1), R(0)); u = x1; v = z1; break;
-        case 2: nm = mk<R>(R(-1), R(0), R(0)); u = y1; v = z1; break;
-        case 3: nm = mk<R>(R(1), R(0), R(0)); u = y1; v = z1; break;
-        case 4: nm = mk<R>(R(0), R(0), R(-1)); u = x1; v = y1; break;
-        default: nm = mk<R>(R(0), R(0), R(1)); u = x1; v = y1; break;
+    } else if (kind == LEAF_CUBE) {
+        if constexpr ((FEAT & FT_CUBE) != 0) {
+            const R x1 = pm.x + R(0.5), y1 = pm.y + R(0.5), z1 = pm.z + R(0.5);
+            const int axis = h.sub >> 1;             // 0: y (bottom/top), 1: x (left/right), 2: z (front/back)
+            const R sgn = (h.sub & 1) ? R(1) : R(-1);  // Cube.fs:18-23: outward normals
+            nm = mk<R>(axis == 1 ? sgn : R(0), axis == 0 ? sgn : R(0), axis == 2 ? sgn : R(0));
+            u = axis == 1 ? y1 : x1;
+            v = axis == 2 ? y1 : z1;
         }
-        break;
-    }
-    case LEAF_TRIANGLE: case LEAF_MESH: {
-        const int tri = (kind == LEAF_TRIANGLE) ? meta.w : h.sub;
-        R4 a1 = ldg4<R>(S.tris + 3 * tri + 1), a2 = ldg4<R>(S.tris + 3 * tri + 2);
-        nm = normalise(cross(mk<R>(a1.x, a1.y, a1.z), mk<R>(a2.x, a2.y, a2.z)));
-        break;
-    }
+    } else if (kind == LEAF_CYLINDER || kind == LEAF_CONE) {
+        if constexpr ((FEAT & FT_ROUND) != 0) {
+            Vec<R> n = normalise(mk<R>(pm.x, kind == LEAF_CONE ? -(pm.y - R(1)) : R(0), pm.z));
+            nm = (dot(n, r.d) < R(0)) ? n : -n;  // Cylinder.fs:17, Cone.fs:24: always faces the ray
+        }
+    } else {  // LEAF_TRIANGLE, LEAF_MESH
+        if constexpr ((FEAT & FT_MESH) != 0) {
+            const int tri = (kind == LEAF_TRIANGLE) ? meta.w : h.sub;
+            R4 a1 = ldg4<R>(S.tris + 3 * tri + 1), a2 = ldg4<R>(S.tris + 3 * tri + 2);
+            nm = normalise(cross(mk<R>(a1.x, a1.y, a1.z), mk<R>(a2.x, a2.y, a2.z)));
+        }
     }
     Fragment<R> f;
     const int4 si = __ldg(S.surf_i + meta.y);
-    if (si.x >= 0 && kind == LEAF_SPHERE) {  // Sphere.setUV (Sphere.fs:6-10), only needed when textured
-        u = R(0.5) + (atan2_(nm.z, nm.x) / (R(2) * R(3.14159265358979323846)));
-        v = R(0.5) - asin_(nm.y) / R(3.14159265358979323846);
-    }
     // n <- normalise(normalToWorld * n), normalToWorld = transpose(worldToModel) (Transform.fs:83,86)
     Vec<R> nw = nm;
     if (!identity) {
@@ -653,9 +668,15 @@ FTB_DEV Fragment<R> finalise(const DevScene<R>& S, const Ray<R>& wr, const HitIn
     f.p = mk<R>(wr.o.x + h.t * wr.d.x, wr.o.y + h.t * wr.d.y, wr.o.z + h.t * wr.d.z);
     const R4 sa = ldg4<R>(S.surf_a + meta.y), sb = ldg4<R>(S.surf_b + meta.y);
     Vec<R> col = mk<R>(sa.x, sa.y, sa.z);
-    if (si.x >= 0) {
-        col = evalTexture(S, si.x, u, v);
-        for (int k = 0; k < si.y; ++k) col = mk<R>(col.z, col.x, col.y);  // Colour.hueShift (CommonTypes.fs:90)
+    if constexpr ((FEAT & FT_TEX) != 0) {
+        if (si.x >= 0) {
+            if (kind == LEAF_SPHERE) {  // Sphere.setUV (Sphere.fs:6-10), only needed when textured
+                u = R(0.5) + (atan2_(nm.z, nm.x) / (R(2) * R(3.14159265358979323846)));
+                v = R(0.5) - asin_(nm.y) / R(3.14159265358979323846);
+            }
+            col = evalTexture(S, si.x, u, v);
+            for (int k = 0; k < si.y; ++k) col = mk<R>(col.z, col.x, col.y);  // Colour.hueShift (CommonTypes.fs:90)
+        }
     }
     f.colour = col;
     f.roughness = sa.w; f.reflectance = sb.x; f.shineyness = sb.y;
@@ -680,74 +701,44 @@ FTB_DEV Vec<R> roughDiffuse(const Fragment<R>& f, Vec<R> lightDir, Vec<R> viewD)
     return intensity * f.colour;
 }
 
-// One level of getColourForRay (Shading.fs:131-139) minus the recursion: the sum over lights of
-// (specular + diffuse), or of material.colour when lighting is off.  `sample`/`depth` key the RNG.
-template <typename R, bool STATS>
-FTB_DEV Vec<R> shadeLocal(const DevScene<R>& S, const Fragment<R>& f, Vec<R> viewD, unsigned long long seed, unsigned long long sample, unsigned depth,
-                          bool& overflow, Counters<STATS>& cn)
+// One light's fragment colour (shadeIfRequired (multiPartShader [specular; diffuse]), Shading.fs:100-107)
+// given its shadow intensity.  The reflection part is carried by the caller's running weight.
+template <typename R, unsigned FEAT>
+FTB_DEV Vec<R> shadeLight(const DevScene<R>& S, const Fragment<R>& f, Vec<R> viewD, int li, R intensity)
 {
     typedef typename V4<R>::type R4;
-    Vec<R> total = mk<R>(R(0), R(0), R(0));
-    const Vec<R> shadowRayOrigin = f.p + R(0.0001) * f.n;  // Shading.fs:111
-    const Vec<R> viewDirection = normalise(viewD);
-    const Vec<R> normal = normalise(f.n);
-    for (int li = 0; li < S.n_lights; ++li) {
-        const int2 lk = __ldg(S.light_i + li);
-        const R4 la = ldg4<R>(S.light_a + li), lc = ldg4<R>(S.light_c + li);
-        const Vec<R> lv = mk<R>(la.x, la.y, la.z);
-        R intensity;  // shadowLightIntensity (Shading.fs:33-42)
-        Vec<R> ldir;  // lightDirection (Shading.fs:44-48)
-        Ray<R> sr;
-        sr.o = shadowRayOrigin;
-        if (lk.x == FTB_LIGHT_DIRECTIONAL) {
-            sr.d = -lv;
-            intensity = traceAny<R, STATS>(S, sr, realmax_<R>(), overflow, cn) ? R(0) : R(1);
-            ldir = lv;
-        } else if (lk.x == FTB_LIGHT_SOFT_DIRECTIONAL) {  // softShadowLightIntensity (Shading.fs:24-31)
-            int occluded = 0;
-            for (int k = 0; k < lk.y; ++k) {
-                sr.d = jitterVector<R>(seed, sample, depth, (unsigned)li, (unsigned)k, la.w, -lv);
-                if (traceAny<R, STATS>(S, sr, realmax_<R>(), overflow, cn)) ++occluded;
-            }
-            intensity = (R)(lk.y - occluded) / (R)lk.y;
-            ldir = lv;
-        } else {
-            const R4 lb = ldg4<R>(S.light_b + li);
-            const Vec<R> dvec = lv - shadowRayOrigin;
-            const R distance = length(dvec);
-            sr.d = normalise(dvec);
-            if (traceAny<R, STATS>(S, sr, distance, overflow, cn)) intensity = R(0);
-            else intensity = R(1) / (lb.x + distance * (lb.y + distance * lb.z));  // Light.attenuate (Light.fs:16-17)
-            ldir = normalise(f.p - lv);
-        }
-        const Vec<R> lightColour = mk<R>(intensity * lc.x, intensity * lc.y, intensity * lc.z);
-        if (!f.applyLighting) {  // shadeIfRequired (Shading.fs:100-104)
-            total = total + f.colour;
-            continue;
-        }
-        Vec<R> acc = mk<R>(R(0), R(0), R(0));
-        {  // specularShader (Shading.fs:78-87)
-            const Vec<R> reflectedLightDirection = normalise(reflect(normal, ldir));
+    if (!f.applyLighting) return f.colour;  // shadeIfRequired (Shading.fs:100-104)
+    const int2 lk = __ldg(S.light_i + li);
+    const R4 la = ldg4<R>(S.light_a + li), lc = ldg4<R>(S.light_c + li);
+    const Vec<R> lv = mk<R>(la.x, la.y, la.z);
+    const Vec<R> ldir = (lk.x == FTB_LIGHT_POINT) ? normalise(f.p - lv) : lv;  // lightDirection (Shading.fs:44-48): uses p, not the offset origin
+    const Vec<R> lightColour = mk<R>(intensity * lc.x, intensity * lc.y, intensity * lc.z);
+    Vec<R> acc = mk<R>(R(0), R(0), R(0));
+    {  // specularShader (Shading.fs:78-87)
+        const Vec<R> normal = normalise(f.n);
+        const Vec<R> reflectedLightDirection = normalise(reflect(normal, ldir));
+        const Vec<R> viewDirection = normalise(viewD);
+        if (f.shineyness > R(0)) {
             const R si = pow_(dot(viewDirection, -reflectedLightDirection), f.shineyness);
-            if (!(f.shineyness <= R(0) || si <= R(0))) acc = acc + mk<R>(lightColour.x * si, lightColour.y * si, lightColour.z * si);
+            if (!(si <= R(0))) acc = acc + mk<R>(lightColour.x * si, lightColour.y * si, lightColour.z * si);
         }
-        if (f.roughness == R(0)) {  // lambertianDiffuse (Shading.fs:65-70)
-            const R di = dot(-ldir, f.n);
-            acc = acc + mk<R>(di * (f.colour.x * lightColour.x), di * (f.colour.y * lightColour.y), di * (f.colour.z * lightColour.z));
-        } else {
-            acc = acc + roughDiffuse(f, ldir, viewD);
-        }
-        total = total + acc;
     }
-    return total;
+    bool lambert = true;
+    if constexpr ((FEAT & FT_ROUGH) != 0) {
+        if (f.roughness != R(0)) { acc = acc + roughDiffuse(f, ldir, viewD); lambert = false; }
+    }
+    if (lambert) {  // lambertianDiffuse (Shading.fs:65-70), unclamped
+        const R di = dot(-ldir, f.n);
+        acc = acc + mk<R>(di * (f.colour.x * lightColour.x), di * (f.colour.y * lightColour.y), di * (f.colour.z * lightColour.z));
+    }
+    return acc;
 }
 
 // ---- Image.fs (sampling half) -----------------------------------------------------------------------------------
-template <typename R>
+template <typename R, unsigned FEAT>
 FTB_DEV Ray<R> primaryRay(const DevFrame<R>& F, int px, int py, int s, unsigned long long sampleIndex)
 {
-    const R jitterX = (F.spp > 0 && F.jitter) ? __ldg(F.jitter + 2 * s) : R(0);
-    const R jitterY = (F.spp > 0 && F.jitter) ? __ldg(F.jitter + 2 * s + 1) : R(0);
+    const R jitterX = __ldg(F.jitter + 2 * s), jitterY = __ldg(F.jitter + 2 * s + 1);
     // rayThroughPixel (Image.fs:83-89)
     const R centreX = F.tlx + (R)px * F.pw, centreY = F.tly - (R)py * F.ph;
     const R jx = centreX + jitterX * F.pw, jy = centreY + jitterY * F.ph;
@@ -755,43 +746,55 @@ FTB_DEV Ray<R> primaryRay(const DevFrame<R>& F, int px, int py, int s, unsigned 
     Ray<R> r;
     r.o = mk<R>(F.cam_o[0], F.cam_o[1], F.cam_o[2]);
     r.d = (k + jx * i) + jy * j;
-    if (F.has_focus) {  // depthOfFieldJitter (Image.fs:91-94, Ray.fs:15-18)
-        r.o = r.o + F.focal * r.d;
-        r.d = jitterVector<R>(F.seed, sampleIndex, 0u, FTB_RNG_STREAM_CAMERA, 0u, F.tan_half_aperture, r.d);
-        r.o = r.o + (-F.focal) * r.d;
+    if constexpr ((FEAT & FT_RNG) != 0) {
+        if (F.has_focus) {  // depthOfFieldJitter (Image.fs:91-94, Ray.fs:15-18)
+            r.o = r.o + F.focal * r.d;
+            r.d = jitterVector<R>(F.seed, sampleIndex, 0u, FTB_RNG_STREAM_CAMERA, 0u, F.tan_half_aperture, r.d);
+            r.o = r.o + (-F.focal) * r.d;
+        }
     }
     return r;
 }
 
 // ---- the kernel ------------------------------------------------------------------------------------------------------
-template <typename R, bool STATS>
+enum Phase : int { PH_IDLE = 0, PH_NEAREST = 1, PH_SHADOW = 2 };
+
+template <typename R, unsigned FEAT, bool STATS>
 __global__ void __launch_bounds__(kBlockThreads) render_kernel(const DevScene<R> S, const DevFrame<R> F)
 {
+    typedef typename V4<R>::type R4;
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     Counters<STATS> cn;
     bool overflow = false;
 
-    // warp-uniform tile cursor
-    int tile_slot = -1;  // local tile index = value of the atomic counter
-    int tile_x0 = 0, tile_y0 = 0, tile_w = 0, tile_n = 0, tile_pos = 0;
+    // warp-uniform work cursor: one unit = an 8x4 block of a 16x16 tile (mode 0) or 32 rays (mode 1)
+    int unit_slot0 = 0, unit_x0 = 0, unit_y0 = 0, unit_w = 0, unit_n = 0, unit_pos = 0;
     bool exhausted = false;
 
-    // per-lane pixel / path state
-    bool have_pixel = false, active = false;
-    int px = 0, py = 0, slot = 0, s = 0, limit = 0;
-    unsigned depth = 0;
+    // per-lane pixel state
+    bool have_pixel = false;
+    int px = 0, py = 0, slot = 0, s = 0;
     long long unit = 0;  // pixel index in the grid (mode 0) or ray index (mode 1)
     Vec<R> pixsum = mk<R>(R(0), R(0), R(0)), scol = mk<R>(R(0), R(0), R(0));
-    R weight = R(1);
-    Ray<R> ray;
-    ray.o = mk<R>(R(0), R(0), R(0)); ray.d = ray.o;
+    // per-lane path state
+    int phase = PH_IDLE, limit = 0;
+    unsigned depth = 0;
+    R weight = R(1), tmax = R(0);
+    Ray<R> ray;            // the ray to trace next: path ray (un-offset) in PH_NEAREST, shadow ray in PH_SHADOW
+    Vec<R> pathD;          // direction of the current path ray (viewRay.d of the fragment being shaded)
+    ray.o = mk<R>(R(0), R(0), R(0)); ray.d = ray.o; pathD = ray.o;
+    Fragment<R> f;
+    f.p = ray.o; f.n = ray.o; f.colour = ray.o; f.roughness = f.reflectance = f.shineyness = R(0); f.applyLighting = false;
+    Vec<R> local = ray.o;  // sum over lights at the current level
+    int li = 0, sk = 0, occluded = 0;
     const int spp = F.mode == 0 ? F.spp : 1;
+    const int n_units = F.mode == 0 ? F.n_local_tiles * 8 : (int)((F.n_rays + 31) / 32);
 
     for (;;) {
         // ---- re-arm lanes whose path ended -------------------------------------------------------------
-        if (!active && have_pixel) {
+        if (phase == PH_IDLE && have_pixel) {
             pixsum = pixsum + scol;  // Array.average folds from Zero in sample order (Image.fs:115)
             if (s + 1 < spp) {
                 ++s;
@@ -802,69 +805,79 @@ __global__ void __launch_bounds__(kBlockThreads) render_kernel(const DevScene<R>
                 have_pixel = false;
             }
         }
-        bool need = !active && !have_pixel;
+        bool need = phase == PH_IDLE && !have_pixel;
         unsigned m = __ballot_sync(full, need);
         while (m && !exhausted) {
-            if (tile_pos >= tile_n) {  // warp grabs the next tile from the per-GPU queue
+            if (unit_pos >= unit_n) {  // warp grabs the next unit from the per-GPU queue
                 unsigned c = 0;
                 if (lane == 0) c = atomicAdd(F.tile_counter, 1u);
                 c = __shfl_sync(full, c, 0);
-                if (c >= (unsigned)F.n_local_tiles) { exhausted = true; break; }
-                tile_slot = (int)c;
-                tile_pos = 0;
+                if (c >= (unsigned)n_units) { exhausted = true; break; }
+                unit_pos = 0;
                 if (F.mode == 0) {
-                    const int tile = (int)c * F.shard_count + F.shard_index;
-                    tile_x0 = (tile % F.tiles_x) * FTB_TILE_W;
-                    tile_y0 = (tile / F.tiles_x) * FTB_TILE_H;
-                    tile_w = min(FTB_TILE_W, F.gw - tile_x0);
-                    tile_n = tile_w * min(FTB_TILE_H, F.gh - tile_y0);
+                    const int ltile = (int)(c >> 3), sub = (int)(c & 7u);
+                    const int tile = ltile * F.shard_count + F.shard_index;
+                    const int sx = (sub & 1) * 8, sy = (sub >> 1) * 4;
+                    unit_x0 = (tile % F.tiles_x) * FTB_TILE_W + sx;
+                    unit_y0 = (tile / F.tiles_x) * FTB_TILE_H + sy;
+                    unit_slot0 = ltile * FTB_TILE_PIXELS + sy * FTB_TILE_W + sx;
+                    unit_w = max(0, min(8, F.gw - unit_x0));
+                    unit_n = unit_w * max(0, min(4, F.gh - unit_y0));
                 } else {
-                    const long long first = (long long)c * FTB_TILE_PIXELS;
-                    tile_n = (int)min((long long)FTB_TILE_PIXELS, F.n_rays - first);
+                    const long long first = (long long)c * 32;
+                    unit_slot0 = (int)first;
+                    unit_n = (int)min(32LL, F.n_rays - first);
                 }
+                if (unit_n <= 0) continue;
             }
-            // deal the tile's remaining pixels to the lanes that need one (ballot + popc = warp scan)
+            // deal the unit's remaining pixels to the lanes that need one (ballot + popc = warp scan)
             const int rank = __popc(m & lt_mask);
-            const int avail = tile_n - tile_pos;
+            const int avail = unit_n - unit_pos;
             if (need && rank < avail) {
-                const int j = tile_pos + rank;
+                const int j = unit_pos + rank;
                 if (F.mode == 0) {
-                    const int lx = j % tile_w, ly = j / tile_w;
-                    px = tile_x0 + lx; py = tile_y0 + ly;
-                    slot = tile_slot * FTB_TILE_PIXELS + ly * FTB_TILE_W + lx;
+                    const int lx = j % unit_w, ly = j / unit_w;
+                    px = unit_x0 + lx; py = unit_y0 + ly;
+                    slot = unit_slot0 + ly * FTB_TILE_W + lx;
                     unit = (long long)py * F.gw + px;
                 } else {
-                    unit = (long long)tile_slot * FTB_TILE_PIXELS + j;
+                    unit = (long long)unit_slot0 + j;
                     slot = (int)unit;
                 }
                 have_pixel = true; need = false;
                 s = 0;
                 pixsum = mk<R>(R(0), R(0), R(0));
             }
-            tile_pos += min(__popc(m), avail);
+            unit_pos += min(__popc(m), avail);
             m = __ballot_sync(full, need);
         }
-        if (!active && have_pixel) {  // start the next primary sample
-            const unsigned long long sampleIndex = (unsigned long long)unit * (unsigned)spp + (unsigned)s;
-            if (F.mode == 0) ray = primaryRay(F, px, py, s, sampleIndex);
+        const unsigned long long sampleIndex = (unsigned long long)unit * (unsigned)spp + (unsigned)s;
+        if (phase == PH_IDLE && have_pixel) {  // start the next primary sample
+            if (F.mode == 0) ray = primaryRay<R, FEAT>(F, px, py, s, sampleIndex);
             else {
                 const double* q = F.rays + 6 * unit;
                 ray.o = mk<R>((R)__ldg(q), (R)__ldg(q + 1), (R)__ldg(q + 2));
                 ray.d = mk<R>((R)__ldg(q + 3), (R)__ldg(q + 4), (R)__ldg(q + 5));
             }
-            active = true; depth = 0; limit = F.recursion_limit; weight = R(1);
+            phase = PH_NEAREST; depth = 0; limit = F.recursion_limit; weight = R(1);
             scol = mk<R>(R(0), R(0), R(0));
             cn.add(ST_PRIMARY);
         }
-        if (!__any_sync(full, active)) break;
+        if (!__any_sync(full, phase != PH_IDLE)) break;
+        if (phase == PH_IDLE) continue;
 
-        // ---- one generation for every active lane ------------------------------------------------------------
-        if (active) {
-            const unsigned long long sampleIndex = (unsigned long long)unit * (unsigned)spp + (unsigned)s;
-            Ray<R> off;  // slightOffset (Shading.fs:129): d is NOT normalised
-            off.o = ray.o + R(0.0001) * ray.d;
-            off.d = ray.d;
-            const HitInfo<R> h = traceNearest<R, STATS>(S, off, overflow, cn);
+        // ---- trace this lane's current ray: the one expensive step ------------------------------------------------
+        Ray<R> tr = ray;
+        if (phase == PH_NEAREST) {  // slightOffset (Shading.fs:129): d is NOT normalised
+            tr.o = ray.o + R(0.0001) * ray.d;
+            pathD = ray.d;
+        } else cn.add(ST_SHADOW);
+        const HitInfo<R> h = traceScene<R, FEAT, STATS>(S, tr, phase == PH_NEAREST ? inf_<R>() : tmax, phase == PH_SHADOW, overflow, cn);
+
+        // ---- consume the result -----------------------------------------------------------------------------------------
+        bool got = false;       // an intensity for light `li` is ready
+        R intensity = R(0);
+        if (phase == PH_NEAREST) {
             if (depth == 0 && F.dbg_prim) {
                 int prim = -1, sub = 0;
                 if (h.leaf >= 0) {
@@ -877,23 +890,76 @@ __global__ void __launch_bounds__(kBlockThreads) render_kernel(const DevScene<R>
                 if (F.dbg_sub) F.dbg_sub[sampleIndex] = sub;
                 if (F.dbg_t) F.dbg_t[sampleIndex] = h.leaf >= 0 ? (double)h.t : -1.0;
             }
-            bool cont = false;
-            if (h.leaf >= 0 && S.n_lights > 0) {
-                cn.add(ST_SHADED);
-                const Fragment<R> f = finalise(S, off, h);
-                const Vec<R> local = shadeLocal<R, STATS>(S, f, ray.d, F.seed, sampleIndex, depth, overflow, cn);
-                scol = scol + weight * local;
-                // reflectionShader (Shading.fs:89-98) sits inside the per-light sum: L identical re-traces
-                if (f.applyLighting && f.reflectance > R(0) && limit > 0) {
-                    weight = weight * ((R)S.n_lights * f.reflectance);
-                    const Vec<R> rd = reflect(f.n, ray.d);
-                    ray.o = f.p; ray.d = rd;
-                    --limit; ++depth;
-                    cont = true;
-                    cn.add(ST_REFLECTION);
+            if (h.leaf < 0 || S.n_lights <= 0) { phase = PH_IDLE; continue; }  // miss: empty sum (Shading.fs:137-139)
+            cn.add(ST_SHADED);
+            f = finalise<R, FEAT>(S, tr, h);
+            local = mk<R>(R(0), R(0), R(0));
+            li = 0;
+            ray.o = f.p + R(0.0001) * f.n;  // shadowRayOrigin (Shading.fs:111), the same for every light
+        } else {
+            const bool blocked = h.leaf >= 0;
+            const int2 lk = __ldg(S.light_i + li);
+            if (lk.x == FTB_LIGHT_SOFT_DIRECTIONAL) {  // softShadowLightIntensity (Shading.fs:24-31)
+                if constexpr ((FEAT & FT_RNG) != 0) {
+                    occluded += blocked ? 1 : 0;
+                    ++sk;
+                    if (sk < lk.y) {
+                        const R4 la = ldg4<R>(S.light_a + li);
+                        ray.d = jitterVector<R>(F.seed, sampleIndex, depth, (unsigned)li, (unsigned)sk, la.w, -mk<R>(la.x, la.y, la.z));
+                        continue;  // next sample of the same light
+                    }
+                    intensity = (R)(lk.y - occluded) / (R)lk.y;
                 }
+            } else if (lk.x == FTB_LIGHT_POINT) {
+                const R4 lb = ldg4<R>(S.light_b + li);
+                intensity = blocked ? R(0) : R(1) / (lb.x + tmax * (lb.y + tmax * lb.z));  // Light.attenuate (Light.fs:16-17)
+            } else {
+                intensity = blocked ? R(0) : R(1);
             }
-            active = cont;
+            got = true;
+        }
+        // advance through the lights until one needs a shadow ray or the level is complete
+        for (;;) {
+            if (got) { local = local + shadeLight<R, FEAT>(S, f, pathD, li, intensity); ++li; got = false; }
+            if (li >= S.n_lights) break;
+            // fragments whose colour ignores the light's intensity need no shadow ray: unlit surfaces
+            // (shadeIfRequired) and Oren-Nayar surfaces without a specular term (Shading.fs:50-63, 85-86)
+            bool needShadow = f.applyLighting;
+            if constexpr ((FEAT & FT_ROUGH) != 0) needShadow = needShadow && !(f.roughness != R(0) && !(f.shineyness > R(0)));
+            if (!needShadow) { intensity = R(1); got = true; continue; }
+            const int2 lk = __ldg(S.light_i + li);
+            const R4 la = ldg4<R>(S.light_a + li);
+            const Vec<R> lv = mk<R>(la.x, la.y, la.z);
+            if (lk.x == FTB_LIGHT_POINT) {  // shadowLightIntensity (Shading.fs:33-42)
+                const Vec<R> dvec = lv - ray.o;
+                tmax = length(dvec);
+                ray.d = normalise(dvec);
+            } else if (lk.x == FTB_LIGHT_SOFT_DIRECTIONAL) {
+                if (lk.y <= 0) { intensity = (R)(lk.y - 0) / (R)lk.y; got = true; continue; }  // 0/0: NaN like the reference
+                if constexpr ((FEAT & FT_RNG) != 0) {
+                    sk = 0; occluded = 0;
+                    tmax = realmax_<R>();
+                    ray.d = jitterVector<R>(F.seed, sampleIndex, depth, (unsigned)li, 0u, la.w, -lv);
+                }
+            } else {
+                tmax = realmax_<R>();
+                ray.d = -lv;
+            }
+            phase = PH_SHADOW;
+            break;
+        }
+        if (li < S.n_lights) continue;  // a shadow ray is pending
+        // ---- level complete (getColourForRay's Seq.sumBy, Shading.fs:139) -----------------------------------------------
+        scol = scol + weight * local;
+        // reflectionShader (Shading.fs:89-98) sits inside the per-light sum: L identical re-traces => weight L * reflectance
+        if (f.applyLighting && f.reflectance > R(0) && limit > 0) {
+            weight = weight * ((R)S.n_lights * f.reflectance);
+            ray.o = f.p; ray.d = reflect(f.n, pathD);
+            --limit; ++depth;
+            phase = PH_NEAREST;
+            cn.add(ST_REFLECTION);
+        } else {
+            phase = PH_IDLE;
         }
     }
     if (overflow) atomicExch(F.overflow, 1u);
@@ -906,22 +972,32 @@ __global__ void __launch_bounds__(kBlockThreads) render_kernel(const DevScene<R>
     }
 }
 
-template <typename R>
+template <typename R, unsigned FEAT, bool WITH_STATS>
 cudaError_t launch_render_impl(const DevScene<R>& s, const DevFrame<R>& f, bool stats, int sm_count, cudaStream_t stream, int* launches)
 {
     int per_sm = 0;
     cudaError_t e;
-    if (stats) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_kernel<R, true>, kBlockThreads, 0);
-    else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_kernel<R, false>, kBlockThreads, 0);
+    if constexpr (WITH_STATS) {
+        if (stats) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_kernel<R, FEAT, true>, kBlockThreads, 0);
+        else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_kernel<R, FEAT, false>, kBlockThreads, 0);
+    } else {
+        if (stats) return cudaErrorInvalidValue;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_kernel<R, FEAT, false>, kBlockThreads, 0);
+    }
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
-    // persistent grid: a multiple of the SM count, never more warps than there are tiles to hand out
+    // persistent grid: a multiple of the SM count, never more warps than there are work units to hand out
+    const long long units = f.mode == 0 ? (long long)f.n_local_tiles * 8 : (f.n_rays + 31) / 32;
     long long want = (long long)sm_count * per_sm;
-    long long cap = ((long long)f.n_local_tiles + (kBlockThreads / 32) - 1) / (kBlockThreads / 32);
+    long long cap = (units + (kBlockThreads / 32) - 1) / (kBlockThreads / 32);
     int grid = (int)(want < cap ? want : cap);
     if (grid < 1) grid = 1;
-    if (stats) render_kernel<R, true><<<grid, kBlockThreads, 0, stream>>>(s, f);
-    else render_kernel<R, false><<<grid, kBlockThreads, 0, stream>>>(s, f);
+    if constexpr (WITH_STATS) {
+        if (stats) render_kernel<R, FEAT, true><<<grid, kBlockThreads, 0, stream>>>(s, f);
+        else render_kernel<R, FEAT, false><<<grid, kBlockThreads, 0, stream>>>(s, f);
+    } else {
+        render_kernel<R, FEAT, false><<<grid, kBlockThreads, 0, stream>>>(s, f);
+    }
     if (launches) ++*launches;
     return cudaGetLastError();
 }

@@ -191,8 +191,8 @@ def test_stats_counters_against_oracle():
 
 def test_hit_overflow_is_reported_not_hidden():
     """A CSG operand with more crossings than the per-ray hit stack returns FTB_ERR_HIT_OVERFLOW."""
-    spheres = " ".join("(translate (0,0,%g) sphere)" % (0.1 * i) for i in range(20))
-    text = one_object_scene("(union (group %s) (translate (5,0,0) sphere))" % spheres, "directional dir (0,-1,1) colour 1")
+    col = lambda z0: " ".join("(translate (0,0,%g) sphere)" % (z0 + 0.1 * i) for i in range(10))
+    text = one_object_scene("(union (group %s) (group %s))" % (col(0.0), col(1.0)), "directional dir (0,-1,1) colour 1")
     sc = parse(text)
     with api.Scene(sc) as scene:
         with pytest.raises(api.FtbError) as e:
