@@ -204,6 +204,7 @@ def main():
     import torch
     import torch.distributed as dist
     from functracer_b200 import abi, api
+    from functracer_b200 import dist as fdist
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -258,7 +259,7 @@ def main():
         if ev:
             ev[1].record()
         if world > 1:
-            dist.gather(tiles, gather_list, dst=0)
+            fdist.gather_tiles(tiles, max_bytes, gather_list)
             if rank == 0:
                 api.assemble_device(p_f32, [g.data_ptr() for g in gather_list], frame.data_ptr(), stream=stream)
         else:
@@ -308,7 +309,7 @@ def main():
             scene.render_params(p_host, out=out_np)  # H2D (jitter, frame constants) + kernels + D2H, synchronous
         else:
             scene.render_tiles_device(p_f32, tiles.data_ptr(), stream=stream)
-            dist.gather(tiles, gather_list, dst=0)
+            fdist.gather_tiles(tiles, max_bytes, gather_list)
             if rank == 0:
                 api.assemble_device(p_f64out, [g.data_ptr() for g in gather_list], frame64.data_ptr(), stream=stream)
                 out_host.copy_(frame64, non_blocking=True)
@@ -356,12 +357,13 @@ def main():
         if not args.no_cpu_baseline:
             windows = _sample_windows(W, H, 8, 8)
             rays, secs, cores = cpu_sample(parsed, jit, windows)
-            if secs < 5.0:  # scale the sample towards ~10-30 s of CPU work
-                reps = min(8, max(1, int(10.0 / max(secs, 1e-3))))
-                windows = _sample_windows(W, H, 8 * reps, 8)
+            if secs < 8.0:  # scale the sample towards ~10 s of wall time on all cores, at most the whole frame
+                n = int(min(W // 8, max(8, 8 * 10.0 / max(secs, 1e-3))))
+                windows = _sample_windows(W, H, n, 8) if n < W // 8 else [(0, 0, W, H)]
                 rays, secs, cores = cpu_sample(parsed, jit, windows)
+            frac = sum((x1 - x0) * (y1 - y0) for x0, y0, x1, y1 in windows) / float(W * H)
             line["cpu_baseline"] = {"value": rays / secs / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": "%d full-height stripes of 8 px = %.2f%% of the frame, %.1f s of wall time" % (len(windows), 100.0 * len(windows) * 8 / W, secs)}
+                                    "sample": "%d full-height stripe(s) = %.1f%% of the %dx%d x %d spp frame, %.1f s of wall time" % (len(windows), 100.0 * frac, W, H, spp, secs)}
         print(json.dumps(line))
     scene.close()
     if world > 1:

@@ -1,0 +1,55 @@
+"""Tile sharding contract of the C ABI (include/functracer_b200.h: FTB_TILE_W/H, shard_index/shard_count),
+restated on the host for the multi-process plumbing: which tiles a shard owns, how its tile-major buffer
+is laid out, and how N shard buffers become the row-major frame (what ftb_assemble_device does on the GPU).
+
+Pixels are independent in the reference (Shading.fs:141-147 shades 1000-ray chunks independently), so any
+partition is legal; this one is 16x16 tiles dealt round-robin: tile t belongs to shard t % N and is that
+shard's local tile t // N.
+"""
+import numpy as np
+
+from . import abi
+
+
+def grid(width, height):
+    tx = (width + abi.TILE_W - 1) // abi.TILE_W
+    ty = (height + abi.TILE_H - 1) // abi.TILE_H
+    return tx, ty
+
+
+def local_tiles(width, height, shard_index, shard_count):
+    """Global tile indices owned by a shard, in local order."""
+    tx, ty = grid(width, height)
+    return list(range(shard_index, tx * ty, shard_count))
+
+
+def tile_buffer_elems(width, height, shard_index, shard_count):
+    return len(local_tiles(width, height, shard_index, shard_count)) * abi.TILE_PIXELS * 3
+
+
+def pack(frame, shard_index, shard_count):
+    """Row-major frame [H, W, 3] -> the tile-major buffer a shard would have rendered (pixels of other
+    shards are not touched; padding pixels of edge tiles are zero)."""
+    H, W, _ = frame.shape
+    tx, _ = grid(W, H)
+    tiles = local_tiles(W, H, shard_index, shard_count)
+    buf = np.zeros((len(tiles), abi.TILE_H, abi.TILE_W, 3), dtype=frame.dtype)
+    for k, t in enumerate(tiles):
+        x0, y0 = (t % tx) * abi.TILE_W, (t // tx) * abi.TILE_H
+        blk = frame[y0:y0 + abi.TILE_H, x0:x0 + abi.TILE_W]
+        buf[k, :blk.shape[0], :blk.shape[1]] = blk
+    return buf.reshape(-1)
+
+
+def assemble(buffers, width, height):
+    """N tile-major shard buffers -> row-major frame [H, W, 3] (host twin of ftb_assemble_device)."""
+    n = len(buffers)
+    tx, ty = grid(width, height)
+    out = np.zeros((height, width, 3), dtype=np.asarray(buffers[0]).dtype)
+    for t in range(tx * ty):
+        shard, local = t % n, t // n
+        blk = np.asarray(buffers[shard])[local * abi.TILE_PIXELS * 3:(local + 1) * abi.TILE_PIXELS * 3].reshape(abi.TILE_H, abi.TILE_W, 3)
+        x0, y0 = (t % tx) * abi.TILE_W, (t // tx) * abi.TILE_H
+        h, w = min(abi.TILE_H, height - y0), min(abi.TILE_W, width - x0)
+        out[y0:y0 + h, x0:x0 + w] = blk[:h, :w]
+    return out
