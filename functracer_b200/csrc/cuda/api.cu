@@ -5,9 +5,11 @@
 // returns FTB_ERR_NO_DEVICE.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -183,7 +185,9 @@ struct PerDevice {
     SceneStorage<double> f64;
     cudaStream_t stream = nullptr;  // owned; used by the host-buffer entry points
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, done = nullptr;
-    DevBuf control, jitter, tiles, out, dbg_prim, dbg_sub, dbg_t, rays;
+    DevBuf control, jitter, tiles, out, dbg_prim, dbg_sub, dbg_t, rays, order;
+    std::vector<unsigned char> order_key;  // what the cached tile order was computed for
+    bool order_valid = false;
     std::vector<DevBuf> peer_tiles;  // on the gather device: one per remote shard
 };
 
@@ -251,7 +255,10 @@ int uploadScene(const ftb_scene& sc, SceneStorage<R>& st)
             bounds.push_back(Mk4<R>::make(it.bound_c[0], it.bound_c[1], it.bound_c[2], ri < 0 ? -1.0 : ri * ri));
         }
         for (const CsgOp& op : L.ops) ops.push_back(make_int2(op.kind, op.arg));
-        UP(items, v.items) UP(bounds, v.item_bound) UP(ops, v.ops)
+        std::vector<unsigned> casts((L.items.size() + 31) / 32 + 1, 0u);
+        for (size_t i = 0; i < L.items.size(); ++i)
+            if (L.items[i].casts_shadow) casts[i >> 5] |= 1u << (i & 31);
+        UP(items, v.items) UP(bounds, v.item_bound) UP(ops, v.ops) UP(casts, v.item_casts)
         v.n_items = (int)L.items.size();
     }
     {
@@ -420,6 +427,72 @@ void fillStats(const Control& h, const ftb_scene& sc, ftb_stats* s)
     s->flops += f;
 }
 
+// Longest-processing-time-first tile order.  The persistent kernel hands tiles out from an atomic queue; a lane
+// keeps its pixel for all samples and all bounce generations, so the last tiles handed out set the tail.  A
+// static estimate - the projected bounding spheres of the items, weighted by how much work a hit on them
+// causes (CSG programs, reflective surfaces spawn up to recursion_limit more generations) - puts the costly
+// tiles first, so the tail consists of cheap ones.  Ordering cannot change any pixel: tiles are independent.
+// Returns false when every tile has the same estimate (no order needed).
+bool computeTileOrder(const ftb_scene& sc, const ftb_camera& c, const ftb_render_params& p, const FrameGeom& g, std::vector<int>& order)
+{
+    const double kPiHalf = 1.5707963267948966;
+    V3 o = {c.o[0], c.o[1], c.o[2]}, la = {c.look_at[0], c.look_at[1], c.look_at[2]}, up = {c.up[0], c.up[1], c.up[2]};
+    V3 k = normalise(sub(la, o));
+    V3 i = normalise(cross(up, k));
+    V3 j = cross(k, i);
+    const double height = std::tan(c.fov_y_rad / 2.0) * 2.0, width = height * c.aspect_ratio;
+    const double ph = height / (double)(p.width - 1), pw = width / (double)(p.height - 1);  // Image.fs:71-72 (swapped axes)
+    const double tlx = -width / 2.0 + pw / 2.0, tly = height / 2.0 - ph / 2.0;
+    std::vector<float> cost((size_t)g.n_tiles, 1.0f);
+    bool any = false;
+    auto range = [&](double a, double z, double r, double& lo, double& hi) {
+        const double d2 = a * a + z * z;
+        if (d2 <= r * r) { lo = -1e300; hi = 1e300; return true; }
+        const double th = std::atan2(a, z), al = std::asin(r / std::sqrt(d2));
+        const double t0 = th - al, t1 = th + al;
+        if (t0 >= kPiHalf || t1 <= -kPiHalf) return false;  // entirely behind the image plane
+        lo = t0 <= -kPiHalf ? -1e300 : std::tan(t0);
+        hi = t1 >= kPiHalf ? 1e300 : std::tan(t1);
+        return true;
+    };
+    for (const Item& it : sc.L.items) {
+        if (it.bound_r < 0) continue;  // unbounded (planes): the same everywhere
+        double w = 1.0;
+        bool reflective = false;
+        auto leafWork = [&](int leaf) {
+            const Leaf& lf = sc.L.leaves[leaf];
+            const Surface& sf = sc.L.surfaces[lf.surface];
+            if (sf.apply_lighting && sf.reflectance > 0.0) reflective = true;
+        };
+        if (it.kind == ITEM_LEAF) leafWork(it.a);
+        else {
+            w = 0.0;
+            for (int q = it.a; q < it.a + it.b; ++q)
+                if (sc.L.ops[q].kind == OP_LEAF) { leafWork(sc.L.ops[q].arg); w += 2.0; }
+        }
+        w *= (1.0 + (double)sc.lights.size());                              // a shaded hit adds one shadow ray per light
+        if (reflective) w *= 1.0 + (double)std::max(0, p.recursion_limit);   // and up to `limit` more generations
+        V3 v = {it.bound_c[0] - o.x, it.bound_c[1] - o.y, it.bound_c[2] - o.z};
+        const double x = v.x * i.x + v.y * i.y + v.z * i.z, y = v.x * j.x + v.y * j.y + v.z * j.z, z = v.x * k.x + v.y * k.y + v.z * k.z;
+        double xl, xh, yl, yh;
+        if (!range(x, z, it.bound_r, xl, xh) || !range(y, z, it.bound_r, yl, yh)) continue;
+        // image-plane coordinates -> sample-grid pixels (rayThroughPixel, Image.fs:83-89), one pixel of slack for jitter
+        const double px0 = (xl - tlx) / pw - 1.5, px1 = (xh - tlx) / pw + 1.5, py0 = (tly - yh) / ph - 1.5, py1 = (tly - yl) / ph + 1.5;
+        if (px1 < 0 || py1 < 0 || px0 >= g.gw || py0 >= g.gh) continue;
+        const int tx0 = (int)std::max(0.0, std::floor(px0 / FTB_TILE_W)), tx1 = (int)std::min((double)g.tiles_x - 1, std::floor(px1 / FTB_TILE_W));
+        const int ty0 = (int)std::max(0.0, std::floor(py0 / FTB_TILE_H)), ty1 = (int)std::min((double)g.tiles_y - 1, std::floor(py1 / FTB_TILE_H));
+        for (int ty = ty0; ty <= ty1; ++ty)
+            for (int tx = tx0; tx <= tx1; ++tx) cost[(size_t)ty * g.tiles_x + tx] += (float)w;
+        any = true;
+    }
+    if (!any) return false;
+    order.resize((size_t)g.n_local_tiles);
+    for (int l = 0; l < g.n_local_tiles; ++l) order[l] = l;
+    auto costOf = [&](int l) { return cost[(size_t)l * g.shard_count + g.shard_index]; };
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return costOf(a) > costOf(b); });
+    return true;
+}
+
 // Renders one shard's tiles (mode 0) on the CURRENT device into d_tiles.  Everything is queued on
 // `stream`; nothing here synchronises unless stats are requested.
 template <typename R>
@@ -453,6 +526,24 @@ int launchFrame(ftb_scene* sc, PerDevice* pd, const ftb_camera* cam, const ftb_r
     F.seed = p->seed;
     F.out = static_cast<R*>(d_tiles);
     if (d_dbg) { F.dbg_prim = d_dbg->prim_id; F.dbg_sub = d_dbg->sub_id; F.dbg_t = d_dbg->t; }
+    {  // tile order: cached per (camera, frame geometry, recursion limit); recomputed + uploaded only when they change
+        std::vector<unsigned char> key(sizeof(ftb_camera) + 6 * sizeof(int));
+        std::memcpy(key.data(), cam, sizeof(ftb_camera));
+        const int kk[6] = {p->width, p->height, p->sampling, g.shard_index, g.shard_count, p->recursion_limit};
+        std::memcpy(key.data() + sizeof(ftb_camera), kk, sizeof(kk));
+        if (key != pd->order_key) {
+            std::vector<int> order;
+            pd->order_valid = computeTileOrder(*sc, *cam, *p, g, order);
+            if (pd->order_valid) {
+                CK(pd->order.reserve(order.size() * sizeof(int)));
+                CK(cudaMemcpyAsync(pd->order.p, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+                CK(cudaStreamSynchronize(stream));  // `order` is a pageable local
+            }
+            pd->order_key.swap(key);
+        }
+        static const bool noOrder = std::getenv("FTB_NO_TILE_ORDER") != nullptr;  // A/B switch for measurements
+        F.tile_order = (pd->order_valid && !noOrder) ? static_cast<const int*>(pd->order.p) : nullptr;
+    }
     Control* ctl = static_cast<Control*>(pd->control.p);
     F.tile_counter = &ctl->tile_counter; F.overflow = &ctl->overflow; F.stats = ctl->stats;
     const bool wantStats = stats && p->collect_stats;
@@ -581,7 +672,7 @@ void ftb_scene_destroy(ftb_scene* sc)
         cudaSetDevice(pd->device);
         if (pd->stream) cudaStreamSynchronize(pd->stream);
         pd->f32.release(); pd->f64.release();
-        for (DevBuf* b : {&pd->control, &pd->jitter, &pd->tiles, &pd->out, &pd->dbg_prim, &pd->dbg_sub, &pd->dbg_t, &pd->rays}) b->release();
+        for (DevBuf* b : {&pd->control, &pd->jitter, &pd->tiles, &pd->out, &pd->dbg_prim, &pd->dbg_sub, &pd->dbg_t, &pd->rays, &pd->order}) b->release();
         for (DevBuf& b : pd->peer_tiles) b.release();
         if (pd->ev0) cudaEventDestroy(pd->ev0);
         if (pd->ev1) cudaEventDestroy(pd->ev1);

@@ -61,6 +61,7 @@ struct DevScene {
     // top-level items in enumeration order
     const int4* items;     // x = kind, y = a, z = b, w = casts_shadow
     const R4* item_bound;  // xyz = centre, w = (inflated radius)^2 of a conservative bounding sphere (< 0 unbounded)
+    const unsigned* item_casts;  // bit j of word w: item 32 w + j can block light (something under it has applyLighting)
     int n_items;
     const int2* ops;  // CSG programs: x = kind, y = arg
     // surfaces
@@ -110,6 +111,7 @@ struct DevFrame {
     int* dbg_prim;
     int* dbg_sub;
     double* dbg_t;
+    const int* tile_order;  // mode 0, optional: local tile indices, costliest first (longest-processing-time-first)
     unsigned int* tile_counter;
     unsigned int* overflow;
     unsigned long long* stats;  // ST_COUNT slots (stats kernels only)

@@ -513,42 +513,56 @@ FTB_DEV HitInfo<R> traceScene(const DevScene<R>& S, const Ray<R>& wr, R limit, b
     RaySink<R> best;
     best.limit = limit; best.leaf = -1; best.sub = 0; best.flip = 0; best.any = any; best.cur = 0;
     const R inv_dd = R(1) / dot(wr.d, wr.d);
-    for (int it = 0; it < S.n_items; ++it) {
-        if (any && best.leaf >= 0) break;
-        const int4 item = __ldg(S.items + it);
-        if (any && !item.w) continue;  // nothing under it has applyLighting
-        const R4 bound = ldg4<R>(S.item_bound + it);  // xyz = centre, w = inflated radius^2 (< 0: unbounded)
-        if (bound.w >= R(0)) {
-            cn.add(ST_BOUND_TESTS);
+    for (int base = 0; base < S.n_items; base += 32) {
+        // ---- phase A: which of the next 32 items can this ray's line touch at all?  Branch-free and unrolled:
+        // the loads and the arithmetic of neighbouring items overlap (the serial per-item version spent a third
+        // of its stall samples waiting on these two loads).
+        const int n = min(32, S.n_items - base);
+        unsigned cand = 0;
+#pragma unroll 4
+        for (int j = 0; j < n; ++j) {
+            const R4 bound = ldg4<R>(S.item_bound + base + j);  // xyz = centre, w = inflated radius^2 (< 0: unbounded)
             const Vec<R> oc = mk<R>(bound.x - wr.o.x, bound.y - wr.o.y, bound.z - wr.o.z);
             const R b = dot(oc, wr.d);
             const R tc = b * inv_dd;
             const Vec<R> l = mk<R>(oc.x - tc * wr.d.x, oc.y - tc * wr.d.y, oc.z - tc * wr.d.z);  // centre -> line, perpendicular
             const R oc2 = dot(oc, oc);
-            if (dot(l, l) > bound.w + R(1e-6) * oc2) continue;  // the ray's line misses the bound: no crossing at all
-            if (b < R(0) && oc2 > bound.w) continue;           // bound entirely behind the origin: every crossing has t < 0
+            const bool miss = dot(l, l) > bound.w + R(1e-6) * oc2;  // the ray's line misses the bound: no crossing at all
+            const bool behind = b < R(0) && oc2 > bound.w;          // bound entirely behind the origin: every crossing has t < 0
+            const bool unbounded = bound.w < R(0);
+            cn.add(ST_BOUND_TESTS, unbounded ? 0u : 1u);
+            cand |= (unbounded || !(miss || behind)) ? (1u << j) : 0u;
         }
-        if (item.x == ITEM_LEAF) {
-            best.cur = item.y;
-            intersectLeaf<R, FEAT, STATS>(S, item.y, wr, best, cn);
-        } else if constexpr ((FEAT & FT_CSG) != 0) {
-            HitRec<R> stack[kHitCap];
-            const int n = evalCsg<R, FEAT, STATS>(S, item.y, item.z, wr, stack, overflow, cn);
-            for (int k = 0; k < n; ++k) {  // sorted by t
-                const R ht = stack[k].t;
-                if (!(ht >= R(0))) continue;
-                if (!any) {  // the first t >= 0 is this item's candidate; it wins if it beats best
-                    if (ht < best.limit) {
-                        best.limit = ht; best.leaf = (int)(stack[k].id & kIdLeafMask); best.sub = (int)((stack[k].id >> kIdSubShift) & 7u);
-                        best.flip = (stack[k].id & kIdFlip) ? 1 : 0;
+        if (any) cand &= __ldg(S.item_casts + (base >> 5));  // items with nothing that has applyLighting cannot block (Scene.fs:121)
+        // ---- phase B: this lane's candidates, in enumeration order (lanes walk their own lists) -----------------
+        while (cand) {
+            const int it = base + __ffs(cand) - 1;
+            cand &= cand - 1;
+            const int4 item = __ldg(S.items + it);
+            if (item.x == ITEM_LEAF) {
+                best.cur = item.y;
+                intersectLeaf<R, FEAT, STATS>(S, item.y, wr, best, cn);
+            } else if constexpr ((FEAT & FT_CSG) != 0) {
+                HitRec<R> stack[kHitCap];
+                const int nh = evalCsg<R, FEAT, STATS>(S, item.y, item.z, wr, stack, overflow, cn);
+                for (int k = 0; k < nh; ++k) {  // sorted by t
+                    const R ht = stack[k].t;
+                    if (!(ht >= R(0))) continue;
+                    if (!any) {  // the first t >= 0 is this item's candidate; it wins if it beats best
+                        if (ht < best.limit) {
+                            best.limit = ht; best.leaf = (int)(stack[k].id & kIdLeafMask); best.sub = (int)((stack[k].id >> kIdSubShift) & 7u);
+                            best.flip = (stack[k].id & kIdFlip) ? 1 : 0;
+                        }
+                        break;
                     }
-                    break;
+                    if (!(ht < best.limit)) break;
+                    const int leaf = (int)(stack[k].id & kIdLeafMask);
+                    if (__ldg(S.surf_i + __ldg(S.leaf_meta + leaf).y).z) { best.leaf = leaf; break; }
                 }
-                if (!(ht < best.limit)) break;
-                const int leaf = (int)(stack[k].id & kIdLeafMask);
-                if (__ldg(S.surf_i + __ldg(S.leaf_meta + leaf).y).z) { best.leaf = leaf; break; }
             }
+            if (any && best.leaf >= 0) cand = 0;
         }
+        if (any && best.leaf >= 0) break;
     }
     HitInfo<R> h;
     h.t = best.limit; h.leaf = best.leaf; h.sub = best.sub; h.flip = best.flip;
@@ -757,10 +771,13 @@ FTB_DEV Ray<R> primaryRay(const DevFrame<R>& F, int px, int py, int s, unsigned 
 }
 
 // ---- the kernel ------------------------------------------------------------------------------------------------------
+#ifndef FTB_MIN_BLOCKS
+#define FTB_MIN_BLOCKS 1
+#endif
 enum Phase : int { PH_IDLE = 0, PH_NEAREST = 1, PH_SHADOW = 2 };
 
 template <typename R, unsigned FEAT, bool STATS>
-__global__ void __launch_bounds__(kBlockThreads) render_kernel(const DevScene<R> S, const DevFrame<R> F)
+__global__ void __launch_bounds__(kBlockThreads, FTB_MIN_BLOCKS) render_kernel(const DevScene<R> S, const DevFrame<R> F)
 {
     typedef typename V4<R>::type R4;
     const unsigned full = 0xffffffffu;
@@ -815,7 +832,8 @@ __global__ void __launch_bounds__(kBlockThreads) render_kernel(const DevScene<R>
                 if (c >= (unsigned)n_units) { exhausted = true; break; }
                 unit_pos = 0;
                 if (F.mode == 0) {
-                    const int ltile = (int)(c >> 3), sub = (int)(c & 7u);
+                    const int sub = (int)(c & 7u);
+                    const int ltile = F.tile_order ? __ldg(F.tile_order + (c >> 3)) : (int)(c >> 3);  // costliest tiles first
                     const int tile = ltile * F.shard_count + F.shard_index;
                     const int sx = (sub & 1) * 8, sy = (sub >> 1) * 4;
                     unit_x0 = (tile % F.tiles_x) * FTB_TILE_W + sx;

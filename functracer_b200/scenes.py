@@ -283,6 +283,9 @@ CONFIGS = {
     "cfg3-house": dict(build=house, res=(1920, 1080), spp=16, seed=3),
     "cfg3-night-house": dict(build=night_house, res=(1920, 1080), spp=16, seed=3),
     "cfg4-bunny": dict(build=bunny, res=(3840, 2160), spp=16, seed=4),
+    # the same config with a real BSP (depth is a scene-file argument, bunny.scene:7) and with the full-size mesh
+    "cfg4-bunny-d12": dict(build=bunny, res=(3840, 2160), spp=16, seed=4, kw=dict(depth=12)),
+    "cfg4-bunny-full-d14": dict(build=bunny, res=(3840, 2160), spp=16, seed=4, kw=dict(depth=14, mesh="bunny_full.ply")),
     "cfg5-repeat": dict(build=repeat, res=(7680, 4320), spp=64, seed=5),
     "cfg5-moon": dict(build=moon, res=(7680, 4320), spp=64, seed=5),
 }
@@ -290,4 +293,6 @@ CONFIGS = {
 
 def config_text(name, res=None, spp=None, **kw):
     c = CONFIGS[name]
-    return c["build"](res=res or c["res"], spp=spp or c["spp"], **kw)
+    args = dict(c.get("kw", {}))
+    args.update(kw)
+    return c["build"](res=res or c["res"], spp=spp or c["spp"], **args)
