@@ -27,7 +27,7 @@ def lib():
     """Loads libfunctracer_b200.so (built in-tree by __graft_entry__.build()).  Raises if absent."""
     global _LIB
     if _LIB is None:
-        path = os.path.join(_HERE, "libfunctracer_b200.so")
+        path = os.environ.get("FTB_LIB") or os.path.join(_HERE, "libfunctracer_b200.so")  # FTB_LIB: A/B builds of the same ABI
         if not os.path.exists(path):
             raise RuntimeError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                                "(there is no CPU fallback)" % path)

@@ -288,22 +288,31 @@ int uploadScene(const ftb_scene& sc, SceneStorage<R>& st)
         UP(texels, v.texels) UP(ii, v.img_i)
     }
     {
-        std::vector<int> roots; std::vector<R> aabb; std::vector<int2> links, leaves; std::vector<R4> tris;
-        for (const ftb_mesh& m : sc.meshes) roots.push_back(m.root);
-        for (const ftb_bsp_node& n : sc.bsp_nodes) {
-            for (int k = 0; k < 3; ++k) aabb.push_back((R)n.aabb_min[k]);
-            for (int k = 0; k < 3; ++k) aabb.push_back((R)n.aabb_max[k]);
-            links.push_back(make_int2(n.left, n.right));
+        std::vector<int> roots(L.mesh_root.begin(), L.mesh_root.end()); std::vector<int2> links; std::vector<R4> box, btris, tris;
+        for (const BvhNode& n : L.bvh_nodes) {
+            if (sizeof(R) == 4) {
+                box.push_back(Mk4<R>::make(n.lo[0][0], n.lo[0][1], n.lo[0][2], n.hi[0][0]));
+                box.push_back(Mk4<R>::make(n.hi[0][1], n.hi[0][2], n.lo[1][0], n.lo[1][1]));
+                box.push_back(Mk4<R>::make(n.lo[1][2], n.hi[1][0], n.hi[1][1], n.hi[1][2]));
+            } else {
+                box.push_back(Mk4<R>::make(n.dlo[0][0], n.dlo[0][1], n.dlo[0][2], n.dhi[0][0]));
+                box.push_back(Mk4<R>::make(n.dhi[0][1], n.dhi[0][2], n.dlo[1][0], n.dlo[1][1]));
+                box.push_back(Mk4<R>::make(n.dlo[1][2], n.dhi[1][0], n.dhi[1][1], n.dhi[1][2]));
+            }
+            links.push_back(make_int2(n.child[0], n.child[1]));
         }
-        for (const ftb_bsp_leaf& l : sc.bsp_leaves) leaves.push_back(make_int2(l.tri_first, l.tri_count));
         const size_t nt = sc.triangles.size() / 9;
-        for (size_t t = 0; t < nt; ++t) {  // v0, e1 = v1 - v0, e2 = v2 - v0 (Triangle.fs:45-46), differences taken in double
+        auto pushTri = [&](std::vector<R4>& dst, size_t t, double w0, double w1) {  // v0, e1 = v1 - v0, e2 = v2 - v0 (Triangle.fs:45-46), differences taken in double
             const double* q = sc.triangles.data() + 9 * t;
-            tris.push_back(Mk4<R>::make(q[0], q[1], q[2], 0));
-            tris.push_back(Mk4<R>::make(q[3] - q[0], q[4] - q[1], q[5] - q[2], 0));
-            tris.push_back(Mk4<R>::make(q[6] - q[0], q[7] - q[1], q[8] - q[2], 0));
-        }
-        UP(roots, v.mesh_root) UP(aabb, v.bsp_aabb) UP(links, v.bsp_links) UP(leaves, v.bsp_leaves) UP(tris, v.tris)
+            dst.push_back(Mk4<R>::make(q[0], q[1], q[2], w0));
+            dst.push_back(Mk4<R>::make(q[3] - q[0], q[4] - q[1], q[5] - q[2], w1));
+            dst.push_back(Mk4<R>::make(q[6] - q[0], q[7] - q[1], q[8] - q[2], 0));
+        };
+        for (size_t t = 0; t < nt; ++t) pushTri(tris, t, 0, 0);
+        // slot ids ride in the w components as reals: exact up to 2^24 in float
+        if (sizeof(R) == 4 && (L.bvh_tri.size() >= (1u << 24) || nt >= (1u << 24))) return fail(FTB_ERR_UNSUPPORTED, "more than 16M mesh triangles");
+        for (size_t k = 0; k < L.bvh_tri.size(); ++k) pushTri(btris, (size_t)L.bvh_tri[k], (double)L.bvh_seq[k], (double)L.bvh_tri[k]);
+        UP(roots, v.mesh_root) UP(box, v.bvh_box) UP(links, v.bvh_links) UP(btris, v.bvh_tris) UP(tris, v.tris)
     }
     {
         std::vector<int2> li; std::vector<R4> la, lb, lc;
@@ -635,7 +644,7 @@ int ftb_scene_create(const ftb_scene_desc* desc, ftb_scene** out)
     int rc = ftb::lower_scene(*desc, sc->L, err);
     if (rc != FTB_OK) return fail(rc, err);
     if (sc->L.max_csg_lists > ftb::kMaxLists) return fail(FTB_ERR_UNSUPPORTED, "CSG nesting needs more than 12 pending hit lists");
-    if (sc->L.max_bsp_depth + 1 > ftb::kBspStack) return fail(FTB_ERR_UNSUPPORTED, "BSP tree deeper than the 64-entry traversal stack");
+    if (sc->L.max_bvh_depth + 2 > ftb::kBspStack) return fail(FTB_ERR_UNSUPPORTED, "mesh index deeper than the 64-entry traversal stack");
     if (sc->L.leaves.size() >= (1u << 22)) return fail(FTB_ERR_UNSUPPORTED, "more than 4M leaves");
     sc->bsp_nodes.assign(desc->bsp_nodes, desc->bsp_nodes + desc->n_bsp_nodes);
     sc->bsp_leaves.assign(desc->bsp_leaves, desc->bsp_leaves + desc->n_bsp_leaves);

@@ -76,12 +76,12 @@ struct DevScene {
     const R* texop_ab;  // 2 per op
     const uchar4* texels;
     const int4* img_i;  // x = first texel, y = width, z = height
-    // meshes
-    const int* mesh_root;
-    const R* bsp_aabb;  // 6 per node: min.xyz, max.xyz
-    const int2* bsp_links;   // x = left, y = right (>= 0 branch, < 0 ~leaf)
-    const int2* bsp_leaves;  // x = first triangle, y = count
-    const R4* tris;          // 3 per triangle: v0, e1 = v1 - v0, e2 = v2 - v0
+    // meshes: the device's own BVH over each mesh's triangles (lower.h BvhNode)
+    const int* mesh_root;    // per mesh: root link (>= 0 node, < 0 ~((first << 3) | count))
+    const R4* bvh_box;       // 3 per node: (L.lo.xyz, L.hi.x) (L.hi.yz, R.lo.xy) (R.lo.z, R.hi.xyz)
+    const int2* bvh_links;   // per node: child links
+    const R4* bvh_tris;      // 3 per slot: (v0, seq) (e1, triangle index) (e2, -); the ints stored as reals
+    const R4* tris;          // 3 per scene triangle: v0, e1 = v1 - v0, e2 = v2 - v0 (LEAF_TRIANGLE, normals)
     // lights
     const int2* light_i;  // kind, samples
     const R4* light_a;    // v.xyz (dir or pos), tan(scatter / 2)

@@ -279,6 +279,8 @@ struct Lowerer {
             int depth = bspDepth(d.meshes[n.b].root, 0);
             if (status != FTB_OK) return false;
             L.max_bsp_depth = std::max(L.max_bsp_depth, depth);
+            if (L.mesh_used.size() < (size_t)d.n_meshes) L.mesh_used.resize((size_t)d.n_meshes, 0);
+            L.mesh_used[n.b] = 1;
             std::vector<std::array<double, 3>> pts;
             bspPoints(d.meshes[n.b].root, pts);
             out.push_back(addLeaf(LEAF_MESH, cx, cx.w2m, surface, prim, n.b, pts, true));
@@ -418,6 +420,152 @@ struct Lowerer {
 
 }  // namespace
 
+namespace {
+
+// ---- BVH over a mesh's triangles (binned SAH, leaves of <= 4 triangles) ---------------------------------------
+struct Box {
+    double lo[3], hi[3];
+    void reset() { for (int k = 0; k < 3; ++k) { lo[k] = 1e300; hi[k] = -1e300; } }
+    void add(const double* p) { for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], p[k]); hi[k] = std::max(hi[k], p[k]); } }
+    void add(const Box& b) { for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], b.lo[k]); hi[k] = std::max(hi[k], b.hi[k]); } }
+    double area() const
+    {
+        double e[3] = {hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]};
+        if (e[0] < 0) return 0;
+        return 2.0 * (e[0] * e[1] + e[1] * e[2] + e[2] * e[0]);
+    }
+};
+
+struct BvhBuilder {
+    const double* tris;            // scene triangles, 9 doubles each
+    std::vector<int32_t> ref;      // triangle indices being partitioned
+    std::vector<Box> tbox;         // per ref position
+    std::vector<double> cen;       // 3 per ref position
+    Lowered& L;
+    int slotBase;
+    int maxDepth = 0;
+
+    BvhBuilder(const double* t, Lowered& l) : tris(t), L(l), slotBase(0) {}
+
+    Box boxOf(int b, int e) const
+    {
+        Box x; x.reset();
+        for (int i = b; i < e; ++i) x.add(tbox[i]);
+        return x;
+    }
+    void swapRef(int a, int b)
+    {
+        std::swap(ref[a], ref[b]); std::swap(tbox[a], tbox[b]);
+        for (int k = 0; k < 3; ++k) std::swap(cen[3 * a + k], cen[3 * b + k]);
+    }
+    int build(int b, int e, int depth)
+    {
+        maxDepth = std::max(maxDepth, depth);
+        const int n = e - b;
+        if (n <= 4 || depth >= 60) {
+            if (n > 7) {  // depth cap with a fat run: split it into a chain so that every leaf holds <= 4 (count has 3 bits)
+                const int mid = b + 4;
+                return makeNode(b, mid, e, depth);
+            }
+            return ~(((slotBase + b) << 3) | n);
+        }
+        Box cb; cb.reset();
+        for (int i = b; i < e; ++i) cb.add(&cen[3 * i]);
+        int axis = 0;
+        double ext = -1;
+        for (int k = 0; k < 3; ++k) if (cb.hi[k] - cb.lo[k] > ext) { ext = cb.hi[k] - cb.lo[k]; axis = k; }
+        int mid = -1;
+        if (ext > 0) {  // binned SAH on the widest centroid axis
+            const int NB = 16;
+            Box bb[NB]; int cnt[NB];
+            for (int k = 0; k < NB; ++k) { bb[k].reset(); cnt[k] = 0; }
+            const double scale = NB / ext;
+            auto binOf = [&](int i) { int q = (int)((cen[3 * i + axis] - cb.lo[axis]) * scale); return q < 0 ? 0 : (q >= NB ? NB - 1 : q); };
+            for (int i = b; i < e; ++i) { int q = binOf(i); bb[q].add(tbox[i]); ++cnt[q]; }
+            double rightArea[NB]; int rightCnt[NB];
+            Box acc; acc.reset(); int c = 0;
+            for (int k = NB - 1; k > 0; --k) { acc.add(bb[k]); c += cnt[k]; rightArea[k] = acc.area(); rightCnt[k] = c; }
+            acc.reset(); c = 0;
+            double best = 1e300; int bestK = -1;
+            for (int k = 0; k < NB - 1; ++k) {
+                acc.add(bb[k]); c += cnt[k];
+                if (c == 0 || rightCnt[k + 1] == 0) continue;
+                const double cost = acc.area() * c + rightArea[k + 1] * rightCnt[k + 1];
+                if (cost < best) { best = cost; bestK = k; }
+            }
+            if (bestK >= 0) {
+                int i = b, j = e - 1;
+                while (i <= j) { if (binOf(i) <= bestK) ++i; else { swapRef(i, j); --j; } }
+                mid = i;
+            }
+        }
+        if (mid <= b || mid >= e) {  // all centroids coincide (or SAH found nothing): split the run in half
+            mid = b + n / 2;
+        }
+        return makeNode(b, mid, e, depth);
+    }
+    int makeNode(int b, int mid, int e, int depth)
+    {
+        const int idx = (int)L.bvh_nodes.size();
+        L.bvh_nodes.push_back(BvhNode());
+        const int l = build(b, mid, depth + 1);
+        const int r = build(mid, e, depth + 1);
+        const Box lb = boxOf(b, mid), rb = boxOf(mid, e);
+        BvhNode& nd = L.bvh_nodes[idx];
+        nd.child[0] = l; nd.child[1] = r;
+        const Box* bx[2] = {&lb, &rb};
+        for (int c = 0; c < 2; ++c)
+            for (int k = 0; k < 3; ++k) {
+                nd.dlo[c][k] = bx[c]->lo[k]; nd.dhi[c][k] = bx[c]->hi[k];
+                float flo = (float)bx[c]->lo[k], fhi = (float)bx[c]->hi[k];  // round outward
+                if ((double)flo > bx[c]->lo[k]) flo = std::nextafterf(flo, -INFINITY);
+                if ((double)fhi < bx[c]->hi[k]) fhi = std::nextafterf(fhi, INFINITY);
+                nd.lo[c][k] = flo; nd.hi[c][k] = fhi;
+            }
+        return idx;
+    }
+};
+
+// triangles of a reference BSP in BspMesh.intersect's enumeration order: right subtree, then left (BspMesh.fs:72-75)
+void enumerateBsp(const ftb_scene_desc& d, int link, std::vector<int32_t>& out, int depth)
+{
+    if (depth > 300) return;
+    if (link < 0) {
+        const ftb_bsp_leaf& lf = d.bsp_leaves[~link];
+        for (int i = 0; i < lf.tri_count; ++i) out.push_back(lf.tri_first + i);
+        return;
+    }
+    enumerateBsp(d, d.bsp_nodes[link].right, out, depth + 1);
+    enumerateBsp(d, d.bsp_nodes[link].left, out, depth + 1);
+}
+
+void buildMeshIndex(const ftb_scene_desc& d, Lowered& L)
+{
+    L.mesh_root.assign((size_t)std::max(0, d.n_meshes), ~0);
+    for (int m = 0; m < d.n_meshes; ++m) {
+        std::vector<int32_t> tri;
+        if ((size_t)m < L.mesh_used.size() && L.mesh_used[m]) enumerateBsp(d, d.meshes[m].root, tri, 0);
+        BvhBuilder bb(d.triangles, L);
+        bb.slotBase = (int)L.bvh_tri.size();
+        bb.ref = tri;
+        const int n = (int)tri.size();
+        std::vector<int32_t> seqOf((size_t)std::max(1, d.n_triangles), 0);
+        bb.tbox.resize(n); bb.cen.resize(3 * (size_t)n);
+        for (int i = 0; i < n; ++i) {
+            const double* t = d.triangles + 9 * (size_t)tri[i];
+            bb.tbox[i].reset();
+            bb.tbox[i].add(t); bb.tbox[i].add(t + 3); bb.tbox[i].add(t + 6);
+            for (int k = 0; k < 3; ++k) bb.cen[3 * i + k] = 0.5 * (bb.tbox[i].lo[k] + bb.tbox[i].hi[k]);
+            seqOf[tri[i]] = i;
+        }
+        L.mesh_root[m] = n == 0 ? ~0 : bb.build(0, n, 0);
+        for (int i = 0; i < n; ++i) { L.bvh_tri.push_back(bb.ref[i]); L.bvh_seq.push_back(seqOf[bb.ref[i]]); }
+        L.max_bvh_depth = std::max(L.max_bvh_depth, bb.maxDepth);
+    }
+}
+
+}  // namespace
+
 int lower_scene(const ftb_scene_desc& d, Lowered& out, std::string& err)
 {
     if (!d.nodes || d.n_nodes <= 0) { err = "scene has no nodes"; return FTB_ERR_BAD_SCENE; }
@@ -463,6 +611,7 @@ int lower_scene(const ftb_scene_desc& d, Lowered& out, std::string& err)
     if (out.has_rough) f |= 0x20;
     if (out.has_soft_light) f |= 0x40;
     out.features = f;
+    if (out.has_mesh) buildMeshIndex(d, out);
     return FTB_OK;
 }
 

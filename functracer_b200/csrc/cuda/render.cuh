@@ -227,34 +227,14 @@ FTB_DEV bool planeT(const Ray<R>& r, R& t, Vec<R>& p)
     return true;
 }
 
-// BoundingBox.intersects (BoundingBox.fs:32-58)
+// Triangle.fs:43-66 with e1, e2 precomputed; returns t or false.  rows = {v0, e1, e2}.
 template <typename R>
-FTB_DEV bool aabbIntersects(const R* __restrict__ bb, const Ray<R>& ray, Vec<R> inv)
-{
-    R bx0 = __ldg(bb + 0), by0 = __ldg(bb + 1), bz0 = __ldg(bb + 2), bx1 = __ldg(bb + 3), by1 = __ldg(bb + 4), bz1 = __ldg(bb + 5);
-    bool sx = inv.x < R(0), sy = inv.y < R(0), sz = inv.z < R(0);
-    R tmin = ((sx ? bx1 : bx0) - ray.o.x) * inv.x;
-    R tmax = ((sx ? bx0 : bx1) - ray.o.x) * inv.x;
-    R tymin = ((sy ? by1 : by0) - ray.o.y) * inv.y;
-    R tymax = ((sy ? by0 : by1) - ray.o.y) * inv.y;
-    if ((tmin > tymax) || (tymin > tmax)) return false;
-    tmin = fsmax(tymin, tmin);
-    tmax = fsmin(tymax, tmax);
-    R tzmin = ((sz ? bz1 : bz0) - ray.o.z) * inv.z;
-    R tzmax = ((sz ? bz0 : bz1) - ray.o.z) * inv.z;
-    if ((tmin > tzmax) || (tzmin > tmax)) return false;
-    tmin = fsmax(tzmin, tmin);
-    tmax = fsmin(tzmax, tmax);
-    return (tmin < inf_<R>()) && (tmax > -inf_<R>());
-}
-
-// Triangle.fs:43-66 with e1, e2 precomputed; returns t or false.
-template <typename R>
-FTB_DEV bool triangleT(const DevScene<R>& S, int tri, const Ray<R>& ray, R& t)
+FTB_DEV bool triangleT(const typename V4<R>::type* rows, const Ray<R>& ray, R& t, typename V4<R>::type& a0, typename V4<R>::type& a1)
 {
     typedef typename V4<R>::type R4;
     const R epsilon = R(0.0000001);
-    R4 a0 = ldg4<R>(S.tris + 3 * tri), a1 = ldg4<R>(S.tris + 3 * tri + 1), a2 = ldg4<R>(S.tris + 3 * tri + 2);
+    a0 = ldg4<R>(rows); a1 = ldg4<R>(rows + 1);
+    const R4 a2 = ldg4<R>(rows + 2);
     Vec<R> v0 = mk<R>(a0.x, a0.y, a0.z), edge1 = mk<R>(a1.x, a1.y, a1.z), edge2 = mk<R>(a2.x, a2.y, a2.z);
     Vec<R> h = cross(ray.d, edge2);
     R a = dot(edge1, h);
@@ -270,6 +250,85 @@ FTB_DEV bool triangleT(const DevScene<R>& S, int tri, const Ray<R>& ray, R& t)
     return t > epsilon;
 }
 
+FTB_DEV float min_(float a, float b) { return fminf(a, b); }
+FTB_DEV double min_(double a, double b) { return fmin(a, b); }
+FTB_DEV float max_(float a, float b) { return fmaxf(a, b); }
+FTB_DEV double max_(double a, double b) { return fmax(a, b); }
+
+// Ray vs. one child box of a BVH node: entry distance, or +inf when the box cannot hold a hit with
+// 0 <= t <= tmax.  fmin / fmax drop the NaNs that 0 * inf produces for rays parallel to a slab; the exit
+// distance is widened by 4 ulp so that rounding can never reject a box that really holds the hit.
+template <typename R>
+FTB_DEV R boxEntry(R lx, R ly, R lz, R hx, R hy, R hz, const Vec<R>& o, const Vec<R>& inv, R tmax)
+{
+    const R x0 = (lx - o.x) * inv.x, x1 = (hx - o.x) * inv.x;
+    const R y0 = (ly - o.y) * inv.y, y1 = (hy - o.y) * inv.y;
+    const R z0 = (lz - o.z) * inv.z, z1 = (hz - o.z) * inv.z;
+    const R tn = max_(max_(min_(x0, x1), min_(y0, y1)), max_(min_(z0, z1), R(0)));
+    R tf = min_(min_(max_(x0, x1), max_(y0, y1)), min_(max_(z0, z1), tmax));
+    tf = tf * (sizeof(R) == 4 ? R(1.0000005) : R(1.0000000000000009)) + (sizeof(R) == 4 ? R(1e-30) : R(0));
+    return tn <= tf ? tn : inf_<R>();
+}
+
+// Nearest / any hit of a mesh (Scene.fs:9 BspMesh): the device's BVH over the mesh's triangles, front to back,
+// culled against the best t so far.  Result = BspMesh.intersect (BspMesh.fs:67-76) followed by Scene.closest
+// (Scene.fs:112-116): smallest t, and among equal t the triangle that comes first in the reference's
+// right-before-left enumeration (`seq`).  limit: only hits with t < limit count (ties with earlier items lose).
+template <typename R, bool STATS>
+FTB_DEV bool intersectMesh(const DevScene<R>& S, int root, const Ray<R>& r, R limit, bool any, R& bt, int& btri, bool& overflow, Counters<STATS>& cn)
+{
+    typedef typename V4<R>::type R4;
+    int stack[kBspStack];
+    R stackT[kBspStack];
+    int sp = 0;
+    int link = root;
+    bt = limit;
+    btri = -1;
+    int bseq = 0x7fffffff;
+    const Vec<R> inv = mk<R>(R(1) / r.d.x, R(1) / r.d.y, R(1) / r.d.z);
+    for (;;) {
+        // ---- descend: inner nodes until a leaf is reached (every lane of the warp is doing box tests here) ----
+        while (link >= 0) {
+            cn.add(ST_BSP_NODES);
+            const R4 b0 = ldg4<R>(S.bvh_box + 3 * link), b1 = ldg4<R>(S.bvh_box + 3 * link + 1), b2 = ldg4<R>(S.bvh_box + 3 * link + 2);
+            const int2 ch = __ldg(S.bvh_links + link);
+            const R tl = boxEntry<R>(b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, r.o, inv, bt);
+            const R tr = boxEntry<R>(b1.z, b1.w, b2.x, b2.y, b2.z, b2.w, r.o, inv, bt);
+            const bool hl = tl < inf_<R>(), hr = tr < inf_<R>();
+            if (hl && hr) {
+                const bool leftFirst = tl <= tr;
+                if (sp < kBspStack) { stack[sp] = leftFirst ? ch.y : ch.x; stackT[sp] = leftFirst ? tr : tl; ++sp; } else overflow = true;
+                link = leftFirst ? ch.x : ch.y;
+            } else if (hl || hr) {
+                link = hl ? ch.x : ch.y;
+            } else {
+                link = 0x7fffffff;  // nothing below: pop
+                break;
+            }
+        }
+        // ---- leaf: a run of <= 7 triangles ---------------------------------------------------------------------------
+        if (link < 0) {
+            const int code = ~link, first = code >> 3, count = code & 7;
+            for (int i = 0; i < count; ++i) {
+                R t; R4 a0, a1;
+                cn.add(ST_TRI_TESTS_IN_MESH);
+                if (triangleT<R>(S.bvh_tris + 3 * (first + i), r, t, a0, a1)) {
+                    const int seq = (int)a0.w;
+                    if (t < bt || (t == bt && btri >= 0 && seq < bseq)) { bt = t; bseq = seq; btri = (int)a1.w; }
+                }
+            }
+            if (any && btri >= 0) return true;
+        }
+        // ---- pop the nearest postponed subtree that can still hold a closer (or tying) hit -------------------------
+        link = 0x7fffffff;
+        while (sp > 0) {
+            --sp;
+            if (stackT[sp] <= bt) { link = stack[sp]; break; }
+        }
+        if (link == 0x7fffffff) break;
+    }
+    return btri >= 0;
+}
 
 // ---- leaf intersection: calls sink.hit(t, sub) for every crossing, in the reference's order ---------
 // sub: cube face 0..5 (Cube.fs:24), triangle index for meshes, else the leaf's payload.
@@ -357,34 +416,16 @@ FTB_DEV void intersectLeaf(const DevScene<R>& S, int leaf, const Ray<R>& wr, Sin
     }
     if constexpr ((FEAT & FT_MESH) != 0) {
         if (kind == LEAF_TRIANGLE) {
-            R t;
-            if (triangleT(S, meta.w, r, t)) sink.hit(t, 0);
+            R t; typename V4<R>::type a0, a1;
+            if (triangleT<R>(S.tris + 3 * meta.w, r, t, a0, a1)) sink.hit(t, 0);
             return;
         }
-        if (kind == LEAF_MESH) {  // BspMesh.intersect (BspMesh.fs:67-76): AABB gate, right subtree, then left
-            int stack[kBspStack];
-            int sp = 0;
-            stack[sp++] = __ldg(S.mesh_root + meta.w);
-            const Vec<R> inv = mk<R>(R(1) / r.d.x, R(1) / r.d.y, R(1) / r.d.z);
-            while (sp > 0) {
-                int link = stack[--sp];
-                if (link < 0) {
-                    const int2 lf = __ldg(S.bsp_leaves + (~link));
-                    for (int i = 0; i < lf.y; ++i) {
-                        R t;
-                        cn.add(ST_TRI_TESTS_IN_MESH);
-                        if (triangleT(S, lf.x + i, r, t)) sink.hit(t, lf.x + i);
-                        if (sink.done()) { sp = 0; break; }
-                    }
-                } else {
-                    cn.add(ST_BSP_NODES);
-                    if (aabbIntersects(S.bsp_aabb + 6 * link, r, inv)) {
-                        const int2 ln = __ldg(S.bsp_links + link);
-                        if (sp + 2 <= kBspStack) { stack[sp++] = ln.x; stack[sp++] = ln.y; }  // right pops first
-                    }
-                }
+        if constexpr (Sink::kIsRay) {
+            if (kind == LEAF_MESH) {
+                R bt; int btri;
+                if (intersectMesh<R, STATS>(S, __ldg(S.mesh_root + meta.w), r, sink.limit, sink.any, bt, btri, sink.overflow, cn)) sink.hit(bt, btri);
+                return;
             }
-            return;
         }
     }
 }
@@ -395,10 +436,12 @@ FTB_DEV void intersectLeaf(const DevScene<R>& S, int leaf, const Ray<R>& wr, Sin
 // surface has applyLighting = true: any hit with 0 <= t < maxDistance.
 template <typename R>
 struct RaySink {
+    static constexpr bool kIsRay = true;
     R limit;
     int leaf, sub, flip;
     int cur;  // leaf being intersected
     bool any;
+    bool overflow;
     FTB_DEV void hit(R ht, int hsub)
     {
         if (ht >= R(0) && ht < limit) { limit = ht; leaf = cur; sub = hsub; flip = 0; }
@@ -414,6 +457,7 @@ struct HitRec {
 constexpr unsigned kIdFlip = 1u << 30, kIdSideB = 1u << 31, kIdSubShift = 22, kIdLeafMask = (1u << 22) - 1;
 template <typename R>
 struct ListSink {
+    static constexpr bool kIsRay = false;
     HitRec<R>* stack;
     int top;
     int cur;
@@ -511,7 +555,7 @@ FTB_DEV HitInfo<R> traceScene(const DevScene<R>& S, const Ray<R>& wr, R limit, b
 {
     typedef typename V4<R>::type R4;
     RaySink<R> best;
-    best.limit = limit; best.leaf = -1; best.sub = 0; best.flip = 0; best.any = any; best.cur = 0;
+    best.limit = limit; best.leaf = -1; best.sub = 0; best.flip = 0; best.any = any; best.cur = 0; best.overflow = false;
     const R inv_dd = R(1) / dot(wr.d, wr.d);
     for (int base = 0; base < S.n_items; base += 32) {
         // ---- phase A: which of the next 32 items can this ray's line touch at all?  Branch-free and unrolled:
@@ -564,6 +608,7 @@ FTB_DEV HitInfo<R> traceScene(const DevScene<R>& S, const Ray<R>& wr, R limit, b
         }
         if (any && best.leaf >= 0) break;
     }
+    overflow = overflow || best.overflow;
     HitInfo<R> h;
     h.t = best.limit; h.leaf = best.leaf; h.sub = best.sub; h.flip = best.flip;
     return h;
@@ -772,7 +817,7 @@ FTB_DEV Ray<R> primaryRay(const DevFrame<R>& F, int px, int py, int s, unsigned 
 
 // ---- the kernel ------------------------------------------------------------------------------------------------------
 #ifndef FTB_MIN_BLOCKS
-#define FTB_MIN_BLOCKS 1
+#define FTB_MIN_BLOCKS 5  // <= 102 registers: 20 warps / SM measured 3-7 % faster than 16 on cfg2 / cfg3 / cfg4
 #endif
 enum Phase : int { PH_IDLE = 0, PH_NEAREST = 1, PH_SHADOW = 2 };
 
