@@ -560,7 +560,14 @@ int launchFrame(ftb_scene* sc, PerDevice* pd, const ftb_camera* cam, const ftb_r
     int launches = 0;
     const Variant<R>* var = pickVariant<R>(sc->L.features | (cam->has_focus ? (unsigned)FT_RNG : 0u), wantStats);
     if (!var) return fail(FTB_ERR_UNSUPPORTED, "no kernel variant covers this scene's feature mask");
-    CK(var->launch(st.view, F, wantStats, pd->sm_count, stream, &launches));
+    // one launch covers at most UnitCap samples per pixel; more samples = more passes over the same tiles, each
+    // continuing the left fold of the previous one (so the blend order is still Array.average's)
+    for (int s_base = 0; s_base < g.spp; s_base += UnitCap<R>::value) {
+        F.s_base = s_base;
+        F.s_count = std::min(UnitCap<R>::value, g.spp - s_base);
+        if (s_base > 0) CK(cudaMemsetAsync(&ctl->tile_counter, 0, sizeof(unsigned int), stream));
+        CK(var->launch(st.view, F, wantStats, pd->sm_count, stream, &launches));
+    }
     if (timeKernel) CK(cudaEventRecord(pd->ev1, stream));
     if (stats) stats->kernel_launches += launches + 1;  // + the control-block memset
     return FTB_OK;
@@ -863,7 +870,7 @@ int ftb_shade_rays(ftb_scene* scene, const double* rays_od, int64_t n, const ftb
         if (!st.ready) { int r2 = uploadScene<R>(*scene, st); if (r2 != FTB_OK) return r2; }
         DevFrame<R> F;
         std::memset(&F, 0, sizeof(F));
-        F.mode = 1; F.spp = 1;
+        F.mode = 1; F.spp = 1; F.s_base = 0; F.s_count = 1;
         F.n_rays = n;
         F.n_local_tiles = (int)((n + FTB_TILE_PIXELS - 1) / FTB_TILE_PIXELS);
         F.shard_count = 1;

@@ -12,6 +12,9 @@ constexpr int kHitCap = 32;    // per-ray CSG hit stack entries
 constexpr int kMaxLists = 12;  // per-ray CSG list stack depth
 constexpr int kBspStack = 64;  // per-ray BSP traversal stack
 constexpr int kBlockThreads = 128;
+// most samples of one unit of the blend ring (render.cuh): a launch covers at most this many samples per pixel,
+// frames with more are rendered in several passes that continue the same left fold
+template <typename R> struct UnitCap { static constexpr int value = sizeof(R) == 4 ? 128 : 64; };
 
 template <typename R>
 struct V4;
@@ -94,7 +97,8 @@ template <typename R>
 struct DevFrame {
     int mode;  // 0 = camera sample grid, 1 = explicit ray list
     int gw, gh;  // sample grid (W x H, or (W+1) x (H+1) in corner mode)
-    int spp;
+    int spp;              // samples per pixel of the whole frame
+    int s_base, s_count;  // this launch renders samples [s_base, s_base + s_count) of every pixel (s_count <= UnitCap)
     int tiles_x;
     int n_local_tiles;  // tiles this shard renders
     int shard_index, shard_count;

@@ -797,7 +797,7 @@ FTB_DEV Vec<R> shadeLight(const DevScene<R>& S, const Fragment<R>& f, Vec<R> vie
 template <typename R, unsigned FEAT>
 FTB_DEV Ray<R> primaryRay(const DevFrame<R>& F, int px, int py, int s, unsigned long long sampleIndex)
 {
-    const R jitterX = __ldg(F.jitter + 2 * s), jitterY = __ldg(F.jitter + 2 * s + 1);
+    const R jitterX = __ldg(F.jitter + 2 * s), jitterY = __ldg(F.jitter + 2 * s + 1);  // s: sample index within the pixel (corner mode: 0)
     // rayThroughPixel (Image.fs:83-89)
     const R centreX = F.tlx + (R)px * F.pw, centreY = F.tly - (R)py * F.ph;
     const R jx = centreX + jitterX * F.pw, jy = centreY + jitterY * F.ph;
@@ -821,26 +821,42 @@ FTB_DEV Ray<R> primaryRay(const DevFrame<R>& F, int px, int py, int s, unsigned 
 #endif
 enum Phase : int { PH_IDLE = 0, PH_NEAREST = 1, PH_SHADOW = 2 };
 
+// Blend ring: every warp keeps kRingSlots units in flight; a unit is a run of pixels of one 8x4 block times the
+// samples of this pass (<= UnitCap<R> samples).  Lanes take SAMPLES, not pixels: the longest sequential chain a lane
+// can be stuck with is one sample's bounce chain, not spp of them, which is what bounds the kernel's tail and its
+// strong scaling.  Finished sample colours are parked in the unit's slot in shared memory; when the last sample of a
+// unit lands, the warp folds each pixel's samples IN SAMPLE ORDER (Array.average folds from Zero, Image.fs:112-116),
+// so the frame does not depend on which lane traced which sample, nor on timing.
+constexpr int kRingSlots = 4;
+
 template <typename R, unsigned FEAT, bool STATS>
 __global__ void __launch_bounds__(kBlockThreads, FTB_MIN_BLOCKS) render_kernel(const DevScene<R> S, const DevFrame<R> F)
 {
     typedef typename V4<R>::type R4;
+    constexpr int CAP = UnitCap<R>::value;
+    constexpr int WARPS = kBlockThreads / 32;
+    __shared__ R ring_col[WARPS][kRingSlots][CAP * 3];
+    __shared__ int ring_hdr[WARPS][kRingSlots][4];  // out slot of the block's pixel 0, block width, first pixel, pixel count
     const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
     Counters<STATS> cn;
     bool overflow = false;
 
-    // warp-uniform work cursor: one unit = an 8x4 block of a 16x16 tile (mode 0) or 32 rays (mode 1)
-    int unit_slot0 = 0, unit_x0 = 0, unit_y0 = 0, unit_w = 0, unit_n = 0, unit_pos = 0;
+    // warp-uniform cursors: the 8x4 block (or 32 rays) taken from the per-GPU queue, and the unit being dealt from it
+    int blk_slot0 = 0, blk_x0 = 0, blk_y0 = 0, blk_w = 1, blk_npix = 0, blk_pos = 0;
+    int u_slot = 0, u_p0 = 0, u_pos = 0, u_n = 0;
+    int remaining[kRingSlots];
+    bool busy[kRingSlots];
+#pragma unroll
+    for (int k = 0; k < kRingSlots; ++k) { remaining[k] = 0; busy[k] = false; }
     bool exhausted = false;
 
-    // per-lane pixel state
-    bool have_pixel = false;
-    int px = 0, py = 0, slot = 0, s = 0;
-    long long unit = 0;  // pixel index in the grid (mode 0) or ray index (mode 1)
-    Vec<R> pixsum = mk<R>(R(0), R(0), R(0)), scol = mk<R>(R(0), R(0), R(0));
-    // per-lane path state
+    // per-lane sample / path state
+    int rs = 0, ridx = 0;            // ring slot and position of the sample this lane is tracing
+    unsigned long long sampleIndex = 0;  // index of the sample in the reference's full-frame ray list (RNG key, debug planes)
+    bool retire = false;             // the path ended in the previous iteration: park its colour
+    Vec<R> scol = mk<R>(R(0), R(0), R(0));
     int phase = PH_IDLE, limit = 0;
     unsigned depth = 0;
     R weight = R(1), tmax = R(0);
@@ -851,80 +867,103 @@ __global__ void __launch_bounds__(kBlockThreads, FTB_MIN_BLOCKS) render_kernel(c
     f.p = ray.o; f.n = ray.o; f.colour = ray.o; f.roughness = f.reflectance = f.shineyness = R(0); f.applyLighting = false;
     Vec<R> local = ray.o;  // sum over lights at the current level
     int li = 0, sk = 0, occluded = 0;
-    const int spp = F.mode == 0 ? F.spp : 1;
-    const int n_units = F.mode == 0 ? F.n_local_tiles * 8 : (int)((F.n_rays + 31) / 32);
+    const int scount = F.mode == 0 ? F.s_count : 1;  // samples per pixel in this pass
+    const int spp = F.mode == 0 ? F.spp : 1;          // samples per pixel of the frame
+    const int ppu = max(1, min(32, CAP / scount));    // pixels per unit
+    const int n_blocks = F.mode == 0 ? F.n_local_tiles * 8 : (int)((F.n_rays + 31) / 32);
 
     for (;;) {
-        // ---- re-arm lanes whose path ended -------------------------------------------------------------
-        if (phase == PH_IDLE && have_pixel) {
-            pixsum = pixsum + scol;  // Array.average folds from Zero in sample order (Image.fs:115)
-            if (s + 1 < spp) {
-                ++s;
-            } else {
-                // DivideByInt (CommonTypes.fs:43)
-                R* o = F.out + 3 * (long long)slot;
-                o[0] = pixsum.x / (R)spp; o[1] = pixsum.y / (R)spp; o[2] = pixsum.z / (R)spp;
-                have_pixel = false;
+        // ---- park finished samples; fold units whose last sample has landed -----------------------------------------
+        if (retire) {
+            R* c = &ring_col[wib][rs][3 * ridx];
+            c[0] = scol.x; c[1] = scol.y; c[2] = scol.z;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < kRingSlots; ++k) {
+            remaining[k] -= __popc(__ballot_sync(full, retire && rs == k));
+            if (busy[k] && remaining[k] == 0) {
+                const int slot0 = ring_hdr[wib][k][0], w = ring_hdr[wib][k][1], p0 = ring_hdr[wib][k][2], np = ring_hdr[wib][k][3];
+                for (int i = lane; i < np * 3; i += 32) {
+                    const int pix = i / 3, ch = i - 3 * pix;
+                    const int pj = p0 + pix;
+                    const long long o = 3 * ((long long)slot0 + (pj / w) * FTB_TILE_W + (pj % w)) + ch;
+                    R acc = F.s_base > 0 ? F.out[o] : R(0);  // a later pass continues the left fold of the earlier ones
+                    const R* c = &ring_col[wib][k][3 * (pix * scount) + ch];
+                    for (int q = 0; q < scount; ++q) acc = acc + c[3 * q];
+                    if (F.s_base + scount >= spp) acc = acc / (R)spp;  // DivideByInt (CommonTypes.fs:43)
+                    F.out[o] = acc;
+                }
+                busy[k] = false;
             }
         }
-        bool need = phase == PH_IDLE && !have_pixel;
+        retire = false;
+        __syncwarp();
+        // ---- deal samples to idle lanes (ballot + popc = warp scan) ---------------------------------------------------
+        bool need = phase == PH_IDLE;
         unsigned m = __ballot_sync(full, need);
         while (m && !exhausted) {
-            if (unit_pos >= unit_n) {  // warp grabs the next unit from the per-GPU queue
-                unsigned c = 0;
-                if (lane == 0) c = atomicAdd(F.tile_counter, 1u);
-                c = __shfl_sync(full, c, 0);
-                if (c >= (unsigned)n_units) { exhausted = true; break; }
-                unit_pos = 0;
-                if (F.mode == 0) {
-                    const int sub = (int)(c & 7u);
-                    const int ltile = F.tile_order ? __ldg(F.tile_order + (c >> 3)) : (int)(c >> 3);  // costliest tiles first
-                    const int tile = ltile * F.shard_count + F.shard_index;
-                    const int sx = (sub & 1) * 8, sy = (sub >> 1) * 4;
-                    unit_x0 = (tile % F.tiles_x) * FTB_TILE_W + sx;
-                    unit_y0 = (tile / F.tiles_x) * FTB_TILE_H + sy;
-                    unit_slot0 = ltile * FTB_TILE_PIXELS + sy * FTB_TILE_W + sx;
-                    unit_w = max(0, min(8, F.gw - unit_x0));
-                    unit_n = unit_w * max(0, min(4, F.gh - unit_y0));
-                } else {
-                    const long long first = (long long)c * 32;
-                    unit_slot0 = (int)first;
-                    unit_n = (int)min(32LL, F.n_rays - first);
+            if (u_pos >= u_n) {  // open the next unit
+                int freeSlot = -1;
+#pragma unroll
+                for (int k = kRingSlots - 1; k >= 0; --k) if (!busy[k]) freeSlot = k;
+                if (freeSlot < 0) break;  // every slot still has a sample in flight: idle lanes wait one iteration
+                if (blk_pos >= blk_npix) {  // the warp takes the next 8x4 block (32 rays) from the per-GPU queue
+                    unsigned c = 0;
+                    if (lane == 0) c = atomicAdd(F.tile_counter, 1u);
+                    c = __shfl_sync(full, c, 0);
+                    if (c >= (unsigned)n_blocks) { exhausted = true; break; }
+                    blk_pos = 0;
+                    if (F.mode == 0) {
+                        const int sub = (int)(c & 7u);
+                        const int ltile = F.tile_order ? __ldg(F.tile_order + (c >> 3)) : (int)(c >> 3);  // costliest tiles first
+                        const int tile = ltile * F.shard_count + F.shard_index;
+                        const int sx = (sub & 1) * 8, sy = (sub >> 1) * 4;
+                        blk_x0 = (tile % F.tiles_x) * FTB_TILE_W + sx;
+                        blk_y0 = (tile / F.tiles_x) * FTB_TILE_H + sy;
+                        blk_slot0 = ltile * FTB_TILE_PIXELS + sy * FTB_TILE_W + sx;
+                        blk_w = max(1, min(8, F.gw - blk_x0));
+                        blk_npix = max(0, min(8, F.gw - blk_x0)) * max(0, min(4, F.gh - blk_y0));
+                    } else {
+                        const long long first = (long long)c * 32;
+                        blk_slot0 = (int)first;
+                        blk_w = 32;
+                        blk_npix = (int)min(32LL, F.n_rays - first);
+                    }
+                    if (blk_npix <= 0) continue;
                 }
-                if (unit_n <= 0) continue;
+                const int np = min(ppu, blk_npix - blk_pos);
+                u_slot = freeSlot; u_p0 = blk_pos; u_pos = 0; u_n = np * scount;
+                blk_pos += np;
+#pragma unroll
+                for (int k = 0; k < kRingSlots; ++k) if (k == freeSlot) { busy[k] = true; remaining[k] = u_n; }
+                if (lane == 0) {
+                    ring_hdr[wib][u_slot][0] = blk_slot0; ring_hdr[wib][u_slot][1] = blk_w; ring_hdr[wib][u_slot][2] = u_p0; ring_hdr[wib][u_slot][3] = np;
+                }
             }
-            // deal the unit's remaining pixels to the lanes that need one (ballot + popc = warp scan)
             const int rank = __popc(m & lt_mask);
-            const int avail = unit_n - unit_pos;
+            const int avail = u_n - u_pos;
             if (need && rank < avail) {
-                const int j = unit_pos + rank;
+                const int j = u_pos + rank;
+                const int pj = u_p0 + j / scount, sj = F.s_base + j % scount;
+                rs = u_slot; ridx = j;
                 if (F.mode == 0) {
-                    const int lx = j % unit_w, ly = j / unit_w;
-                    px = unit_x0 + lx; py = unit_y0 + ly;
-                    slot = unit_slot0 + ly * FTB_TILE_W + lx;
-                    unit = (long long)py * F.gw + px;
+                    const int px = blk_x0 + pj % blk_w, py = blk_y0 + pj / blk_w;
+                    sampleIndex = ((unsigned long long)py * (unsigned)F.gw + (unsigned)px) * (unsigned)spp + (unsigned)sj;
+                    ray = primaryRay<R, FEAT>(F, px, py, sj, sampleIndex);
                 } else {
-                    unit = (long long)unit_slot0 + j;
-                    slot = (int)unit;
+                    sampleIndex = (unsigned long long)blk_slot0 + (unsigned)pj;
+                    const double* q = F.rays + 6 * sampleIndex;
+                    ray.o = mk<R>((R)__ldg(q), (R)__ldg(q + 1), (R)__ldg(q + 2));
+                    ray.d = mk<R>((R)__ldg(q + 3), (R)__ldg(q + 4), (R)__ldg(q + 5));
                 }
-                have_pixel = true; need = false;
-                s = 0;
-                pixsum = mk<R>(R(0), R(0), R(0));
+                phase = PH_NEAREST; depth = 0; limit = F.recursion_limit; weight = R(1);
+                scol = mk<R>(R(0), R(0), R(0));
+                cn.add(ST_PRIMARY);
+                need = false;
             }
-            unit_pos += min(__popc(m), avail);
+            u_pos += min(__popc(m), avail);
             m = __ballot_sync(full, need);
-        }
-        const unsigned long long sampleIndex = (unsigned long long)unit * (unsigned)spp + (unsigned)s;
-        if (phase == PH_IDLE && have_pixel) {  // start the next primary sample
-            if (F.mode == 0) ray = primaryRay<R, FEAT>(F, px, py, s, sampleIndex);
-            else {
-                const double* q = F.rays + 6 * unit;
-                ray.o = mk<R>((R)__ldg(q), (R)__ldg(q + 1), (R)__ldg(q + 2));
-                ray.d = mk<R>((R)__ldg(q + 3), (R)__ldg(q + 4), (R)__ldg(q + 5));
-            }
-            phase = PH_NEAREST; depth = 0; limit = F.recursion_limit; weight = R(1);
-            scol = mk<R>(R(0), R(0), R(0));
-            cn.add(ST_PRIMARY);
         }
         if (!__any_sync(full, phase != PH_IDLE)) break;
         if (phase == PH_IDLE) continue;
@@ -953,7 +992,7 @@ __global__ void __launch_bounds__(kBlockThreads, FTB_MIN_BLOCKS) render_kernel(c
                 if (F.dbg_sub) F.dbg_sub[sampleIndex] = sub;
                 if (F.dbg_t) F.dbg_t[sampleIndex] = h.leaf >= 0 ? (double)h.t : -1.0;
             }
-            if (h.leaf < 0 || S.n_lights <= 0) { phase = PH_IDLE; continue; }  // miss: empty sum (Shading.fs:137-139)
+            if (h.leaf < 0 || S.n_lights <= 0) { phase = PH_IDLE; retire = true; continue; }  // miss: empty sum (Shading.fs:137-139)
             cn.add(ST_SHADED);
             f = finalise<R, FEAT>(S, tr, h);
             local = mk<R>(R(0), R(0), R(0));
@@ -1022,7 +1061,7 @@ __global__ void __launch_bounds__(kBlockThreads, FTB_MIN_BLOCKS) render_kernel(c
             phase = PH_NEAREST;
             cn.add(ST_REFLECTION);
         } else {
-            phase = PH_IDLE;
+            phase = PH_IDLE; retire = true;
         }
     }
     if (overflow) atomicExch(F.overflow, 1u);

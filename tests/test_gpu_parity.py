@@ -207,3 +207,16 @@ def test_determinism():
         a = scene.render(160, 120, 2, jit)["rgb"].copy()
         b = scene.render(160, 120, 2, jit)["rgb"]
     assert (a == b).all()
+
+
+@pytest.mark.parametrize("spp,prec", [(3, abi.PRECISION_FP32), (5, abi.PRECISION_FP64_VERIFY), (16, abi.PRECISION_FP32),
+                                      (33, abi.PRECISION_FP32), (130, abi.PRECISION_FP32), (70, abi.PRECISION_FP64_VERIFY)])
+def test_sample_counts_and_multi_pass_blend(spp, prec):
+    """Samples are dealt to lanes individually and folded per pixel in sample order in shared memory; more than
+    128 (FP32) / 64 (FP64) samples per pixel take several passes that continue the same left fold
+    (Array.average, Image.fs:112-116).  Odd counts exercise units that do not fill a warp."""
+    text = scenes.house(res=(40, 24), spp=spp)
+    ref, got = both(text, precision=prec, jitter_seed=7)
+    check(ref, got, prec, "house-spp%d" % spp)
+    if prec == abi.PRECISION_FP64_VERIFY:
+        assert np.abs(got["rgb"] - ref["rgb"]).max() < 1e-9
