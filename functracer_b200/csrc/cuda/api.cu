@@ -562,9 +562,30 @@ int launchFrame(ftb_scene* sc, PerDevice* pd, const ftb_camera* cam, const ftb_r
     if (!var) return fail(FTB_ERR_UNSUPPORTED, "no kernel variant covers this scene's feature mask");
     // one launch covers at most UnitCap samples per pixel; more samples = more passes over the same tiles, each
     // continuing the left fold of the previous one (so the blend order is still Array.average's)
+    // Work-queue granularity.  A lane takes runs of samples, a warp takes blocks of pixels from the atomic queue.  The
+    // block is the indivisible quantum of the tail, so it shrinks (32 = 8x4 ... 1 pixel) until there are >= 24 blocks
+    // per resident warp, but never below one warp-round of samples per block (and big frames keep big blocks, which
+    // also bounds the number of atomics on the queue counter).
+    {
+        const long long warps = (long long)pd->sm_count * 5 * (kBlockThreads / 32);
+        const long long pixels = (long long)g.n_local_tiles * FTB_TILE_PIXELS;
+        int ppb = 32;
+        while (ppb > 1 && pixels / ppb < 24 * warps && (long long)(ppb / 2) * g.spp >= 32) ppb /= 2;
+        int bw = ppb >= 8 ? 8 : ppb, bh = ppb / bw;
+        F.bw_log = bw == 8 ? 3 : (bw == 4 ? 2 : (bw == 2 ? 1 : 0));
+        F.bh_log = bh == 4 ? 2 : (bh == 2 ? 1 : 0);
+        F.n_blocks = g.n_local_tiles * (FTB_TILE_PIXELS / ppb);
+    }
     for (int s_base = 0; s_base < g.spp; s_base += UnitCap<R>::value) {
         F.s_base = s_base;
         F.s_count = std::min(UnitCap<R>::value, g.spp - s_base);
+        // run length: cheap samples amortise the dealing over up to 8 consecutive samples of a pixel, as long as
+        // every pixel still splits into >= 8 runs (the chain a lane can be stuck with stays 1/8 of a pixel)
+        int run = 1;
+        while (run < 8 && F.s_count % (run * 2) == 0 && F.s_count / (run * 2) >= 8) run *= 2;
+        F.run = run;
+        const unsigned rpp = (unsigned)(F.s_count / run);
+        F.rpp_magic = rpp <= 1 ? 0u : (unsigned)((1ull << 32) / rpp) + 1u;
         if (s_base > 0) CK(cudaMemsetAsync(&ctl->tile_counter, 0, sizeof(unsigned int), stream));
         CK(var->launch(st.view, F, wantStats, pd->sm_count, stream, &launches));
     }
@@ -870,7 +891,8 @@ int ftb_shade_rays(ftb_scene* scene, const double* rays_od, int64_t n, const ftb
         if (!st.ready) { int r2 = uploadScene<R>(*scene, st); if (r2 != FTB_OK) return r2; }
         DevFrame<R> F;
         std::memset(&F, 0, sizeof(F));
-        F.mode = 1; F.spp = 1; F.s_base = 0; F.s_count = 1;
+        F.mode = 1; F.spp = 1; F.s_base = 0; F.s_count = 1; F.run = 1; F.rpp_magic = 0;
+        F.n_blocks = (int)((n + 31) / 32);
         F.n_rays = n;
         F.n_local_tiles = (int)((n + FTB_TILE_PIXELS - 1) / FTB_TILE_PIXELS);
         F.shard_count = 1;

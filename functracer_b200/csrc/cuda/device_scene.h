@@ -99,6 +99,10 @@ struct DevFrame {
     int gw, gh;  // sample grid (W x H, or (W+1) x (H+1) in corner mode)
     int spp;              // samples per pixel of the whole frame
     int s_base, s_count;  // this launch renders samples [s_base, s_base + s_count) of every pixel (s_count <= UnitCap)
+    int run;              // consecutive samples of one pixel a lane takes at a time (divides s_count)
+    unsigned rpp_magic;   // floor(2^32 / (s_count / run)) + 1: q / rpp == __umulhi(q, rpp_magic) for q < 65536
+    int bw_log, bh_log;   // the work queue hands out blocks of (1 << bw_log) x (1 << bh_log) pixels (bw <= 8)
+    int n_blocks;         // blocks (mode 0) or groups of 32 rays (mode 1) in the queue
     int tiles_x;
     int n_local_tiles;  // tiles this shard renders
     int shard_index, shard_count;

@@ -44,7 +44,21 @@ FTB_DEV float abs_(float x) { return fabsf(x); }
 FTB_DEV double abs_(double x) { return fabs(x); }
 FTB_DEV float floor_(float x) { return floorf(x); }
 FTB_DEV double floor_(double x) { return floor(x); }
-FTB_DEV float pow_(float x, float y) { return powf(x, y); }
+// System.Math.Pow semantics that matter to specularShader (Shading.fs:85-87): a negative base with an integral exponent
+// gives +-|x|^y (sign by parity), with a non-integral exponent NaN.  Written out so that the product build can use the
+// hardware exp2/log2 path (-use_fast_math) without losing that quirk.
+FTB_DEV float pow_(float x, float y)
+{
+#ifdef FTB_FAST_MATH
+    if (x >= 0.0f) return __powf(x, y);
+    const float yi = truncf(y);
+    if (yi != y) return CUDART_NAN_F;
+    const float r = __powf(-x, y);
+    return (((int)yi) & 1) ? -r : r;
+#else
+    return powf(x, y);
+#endif
+}
 FTB_DEV double pow_(double x, double y) { return pow(x, y); }
 FTB_DEV float acos_(float x) { return acosf(x); }
 FTB_DEV double acos_(double x) { return acos(x); }
@@ -819,7 +833,7 @@ FTB_DEV Ray<R> primaryRay(const DevFrame<R>& F, int px, int py, int s, unsigned 
 #ifndef FTB_MIN_BLOCKS
 #define FTB_MIN_BLOCKS 5  // <= 102 registers: 20 warps / SM measured 3-7 % faster than 16 on cfg2 / cfg3 / cfg4
 #endif
-enum Phase : int { PH_IDLE = 0, PH_NEAREST = 1, PH_SHADOW = 2 };
+enum Phase : int { PH_IDLE = 0, PH_NEAREST = 1, PH_SHADOW = 2, PH_START = 3 };
 
 // Blend ring: every warp keeps kRingSlots units in flight; a unit is a run of pixels of one 8x4 block times the
 // samples of this pass (<= UnitCap<R> samples).  Lanes take SAMPLES, not pixels: the longest sequential chain a lane
@@ -828,6 +842,27 @@ enum Phase : int { PH_IDLE = 0, PH_NEAREST = 1, PH_SHADOW = 2 };
 // unit lands, the warp folds each pixel's samples IN SAMPLE ORDER (Array.average folds from Zero, Image.fs:112-116),
 // so the frame does not depend on which lane traced which sample, nor on timing.
 constexpr int kRingSlots = 4;
+
+// Folds a completed unit: every pixel's samples of this pass, in sample order, onto the running sum of the earlier
+// passes; the last pass divides by the frame's sample count (Array.average = fold (+) Zero, then DivideByInt;
+// Image.fs:112-116, CommonTypes.fs:43).  One (pixel, channel) per lane.
+template <typename R>
+__device__ __noinline__ void foldUnit(const R* col, const int* hdr, R* out, int scount, int spp, int s_base, int lane)
+{
+    const int slot0 = hdr[0], w = hdr[1], p0 = hdr[2], np = hdr[3];
+    for (int i = lane; i < np * 3; i += 32) {
+        const int pix = i / 3, ch = i - 3 * pix;
+        const int pj = p0 + pix;
+        const int ly = pj / w;
+        const long long o = 3 * ((long long)slot0 + ly * FTB_TILE_W + (pj - ly * w)) + ch;
+        R acc = s_base > 0 ? out[o] : R(0);  // a later pass continues the left fold of the earlier ones
+        const R* c = col + 3 * (pix * scount) + ch;
+#pragma unroll 4
+        for (int q = 0; q < scount; ++q) acc = acc + c[3 * q];
+        if (s_base + scount >= spp) acc = acc / (R)spp;
+        out[o] = acc;
+    }
+}
 
 template <typename R, unsigned FEAT, bool STATS>
 __global__ void __launch_bounds__(kBlockThreads, FTB_MIN_BLOCKS) render_kernel(const DevScene<R> S, const DevFrame<R> F)
@@ -843,9 +878,9 @@ __global__ void __launch_bounds__(kBlockThreads, FTB_MIN_BLOCKS) render_kernel(c
     Counters<STATS> cn;
     bool overflow = false;
 
-    // warp-uniform cursors: the 8x4 block (or 32 rays) taken from the per-GPU queue, and the unit being dealt from it
+    // warp-uniform cursors: the pixel block (or 32 rays) taken from the per-GPU queue, and the unit being dealt from it
     int blk_slot0 = 0, blk_x0 = 0, blk_y0 = 0, blk_w = 1, blk_npix = 0, blk_pos = 0;
-    int u_slot = 0, u_p0 = 0, u_pos = 0, u_n = 0;
+    int u_slot = 0, u_p0 = 0, u_pos = 0, u_n = 0;  // u_pos / u_n count RUNS of F.run consecutive samples of one pixel
     int remaining[kRingSlots];
     bool busy[kRingSlots];
 #pragma unroll
@@ -854,8 +889,9 @@ __global__ void __launch_bounds__(kBlockThreads, FTB_MIN_BLOCKS) render_kernel(c
 
     // per-lane sample / path state
     int rs = 0, ridx = 0;            // ring slot and position of the sample this lane is tracing
+    int px = 0, py = 0, sj = 0, run_left = 0;  // pixel, sample index within the pixel, samples left in this lane's run
     unsigned long long sampleIndex = 0;  // index of the sample in the reference's full-frame ray list (RNG key, debug planes)
-    bool retire = false;             // the path ended in the previous iteration: park its colour
+    bool retire = false;             // a sample of this lane finished in the previous iteration (for the unit's count)
     Vec<R> scol = mk<R>(R(0), R(0), R(0));
     int phase = PH_IDLE, limit = 0;
     unsigned depth = 0;
@@ -869,37 +905,29 @@ __global__ void __launch_bounds__(kBlockThreads, FTB_MIN_BLOCKS) render_kernel(c
     int li = 0, sk = 0, occluded = 0;
     const int scount = F.mode == 0 ? F.s_count : 1;  // samples per pixel in this pass
     const int spp = F.mode == 0 ? F.spp : 1;          // samples per pixel of the frame
+    const int run = F.mode == 0 ? F.run : 1;          // consecutive samples of one pixel a lane takes at a time (divides scount)
+    const int rpp = scount / run;                     // runs per pixel
     const int ppu = max(1, min(32, CAP / scount));    // pixels per unit
-    const int n_blocks = F.mode == 0 ? F.n_local_tiles * 8 : (int)((F.n_rays + 31) / 32);
 
     for (;;) {
-        // ---- park finished samples; fold units whose last sample has landed -----------------------------------------
-        if (retire) {
-            R* c = &ring_col[wib][rs][3 * ridx];
-            c[0] = scol.x; c[1] = scol.y; c[2] = scol.z;
-        }
-        __syncwarp();
+        // ---- fold units whose last sample has landed (colours were parked when each path ended) ---------------------
+        if (__any_sync(full, retire)) {
+            __syncwarp();  // the parked colours of every lane are visible to the lanes that fold
+            unsigned doneSlots = 0;
 #pragma unroll
-        for (int k = 0; k < kRingSlots; ++k) {
-            remaining[k] -= __popc(__ballot_sync(full, retire && rs == k));
-            if (busy[k] && remaining[k] == 0) {
-                const int slot0 = ring_hdr[wib][k][0], w = ring_hdr[wib][k][1], p0 = ring_hdr[wib][k][2], np = ring_hdr[wib][k][3];
-                for (int i = lane; i < np * 3; i += 32) {
-                    const int pix = i / 3, ch = i - 3 * pix;
-                    const int pj = p0 + pix;
-                    const long long o = 3 * ((long long)slot0 + (pj / w) * FTB_TILE_W + (pj % w)) + ch;
-                    R acc = F.s_base > 0 ? F.out[o] : R(0);  // a later pass continues the left fold of the earlier ones
-                    const R* c = &ring_col[wib][k][3 * (pix * scount) + ch];
-                    for (int q = 0; q < scount; ++q) acc = acc + c[3 * q];
-                    if (F.s_base + scount >= spp) acc = acc / (R)spp;  // DivideByInt (CommonTypes.fs:43)
-                    F.out[o] = acc;
-                }
-                busy[k] = false;
+            for (int k = 0; k < kRingSlots; ++k) {
+                remaining[k] -= __popc(__ballot_sync(full, retire && rs == k));
+                if (busy[k] && remaining[k] == 0) { doneSlots |= 1u << k; busy[k] = false; }
             }
+            while (doneSlots) {  // rare relative to the trace: one out-of-line copy keeps the hot loop small
+                const int k = __ffs(doneSlots) - 1;
+                doneSlots &= doneSlots - 1;
+                foldUnit<R>(&ring_col[wib][k][0], &ring_hdr[wib][k][0], F.out, scount, spp, F.s_base, lane);
+            }
+            retire = false;
+            __syncwarp();
         }
-        retire = false;
-        __syncwarp();
-        // ---- deal samples to idle lanes (ballot + popc = warp scan) ---------------------------------------------------
+        // ---- deal runs of samples to idle lanes (ballot + popc = warp scan) -------------------------------------------
         bool need = phase == PH_IDLE;
         unsigned m = __ballot_sync(full, need);
         while (m && !exhausted) {
@@ -908,22 +936,25 @@ __global__ void __launch_bounds__(kBlockThreads, FTB_MIN_BLOCKS) render_kernel(c
 #pragma unroll
                 for (int k = kRingSlots - 1; k >= 0; --k) if (!busy[k]) freeSlot = k;
                 if (freeSlot < 0) break;  // every slot still has a sample in flight: idle lanes wait one iteration
-                if (blk_pos >= blk_npix) {  // the warp takes the next 8x4 block (32 rays) from the per-GPU queue
+                if (blk_pos >= blk_npix) {  // the warp takes the next pixel block (32 rays) from the per-GPU queue
                     unsigned c = 0;
                     if (lane == 0) c = atomicAdd(F.tile_counter, 1u);
                     c = __shfl_sync(full, c, 0);
-                    if (c >= (unsigned)n_blocks) { exhausted = true; break; }
+                    if (c >= (unsigned)F.n_blocks) { exhausted = true; break; }
                     blk_pos = 0;
                     if (F.mode == 0) {
-                        const int sub = (int)(c & 7u);
-                        const int ltile = F.tile_order ? __ldg(F.tile_order + (c >> 3)) : (int)(c >> 3);  // costliest tiles first
+                        // a 16x16 tile holds 2^(8 - bw_log - bh_log) blocks of (1 << bw_log) x (1 << bh_log) pixels
+                        const int bpt_log = 8 - F.bw_log - F.bh_log, bpr_log = 4 - F.bw_log;
+                        const int sub = (int)(c & ((1u << bpt_log) - 1u));
+                        const int tpos = (int)(c >> bpt_log);
+                        const int ltile = F.tile_order ? __ldg(F.tile_order + tpos) : tpos;  // costliest tiles first
                         const int tile = ltile * F.shard_count + F.shard_index;
-                        const int sx = (sub & 1) * 8, sy = (sub >> 1) * 4;
+                        const int sx = (sub & ((1 << bpr_log) - 1)) << F.bw_log, sy = (sub >> bpr_log) << F.bh_log;
                         blk_x0 = (tile % F.tiles_x) * FTB_TILE_W + sx;
                         blk_y0 = (tile / F.tiles_x) * FTB_TILE_H + sy;
                         blk_slot0 = ltile * FTB_TILE_PIXELS + sy * FTB_TILE_W + sx;
-                        blk_w = max(1, min(8, F.gw - blk_x0));
-                        blk_npix = max(0, min(8, F.gw - blk_x0)) * max(0, min(4, F.gh - blk_y0));
+                        blk_w = max(1, min(1 << F.bw_log, F.gw - blk_x0));
+                        blk_npix = max(0, min(1 << F.bw_log, F.gw - blk_x0)) * max(0, min(1 << F.bh_log, F.gh - blk_y0));
                     } else {
                         const long long first = (long long)c * 32;
                         blk_slot0 = (int)first;
@@ -933,10 +964,10 @@ __global__ void __launch_bounds__(kBlockThreads, FTB_MIN_BLOCKS) render_kernel(c
                     if (blk_npix <= 0) continue;
                 }
                 const int np = min(ppu, blk_npix - blk_pos);
-                u_slot = freeSlot; u_p0 = blk_pos; u_pos = 0; u_n = np * scount;
+                u_slot = freeSlot; u_p0 = blk_pos; u_pos = 0; u_n = np * rpp;
                 blk_pos += np;
 #pragma unroll
-                for (int k = 0; k < kRingSlots; ++k) if (k == freeSlot) { busy[k] = true; remaining[k] = u_n; }
+                for (int k = 0; k < kRingSlots; ++k) if (k == freeSlot) { busy[k] = true; remaining[k] = np * scount; }
                 if (lane == 0) {
                     ring_hdr[wib][u_slot][0] = blk_slot0; ring_hdr[wib][u_slot][1] = blk_w; ring_hdr[wib][u_slot][2] = u_p0; ring_hdr[wib][u_slot][3] = np;
                 }
@@ -944,26 +975,34 @@ __global__ void __launch_bounds__(kBlockThreads, FTB_MIN_BLOCKS) render_kernel(c
             const int rank = __popc(m & lt_mask);
             const int avail = u_n - u_pos;
             if (need && rank < avail) {
-                const int j = u_pos + rank;
-                const int pj = u_p0 + j / scount, sj = F.s_base + j % scount;
-                rs = u_slot; ridx = j;
+                const int q = u_pos + rank;                                      // run index within the unit
+                const int pu = rpp == 1 ? q : (int)__umulhi((unsigned)q, F.rpp_magic);  // pixel within the unit = q / rpp
+                const int pj = u_p0 + pu;                                        // pixel within the block
+                sj = F.s_base + (q - pu * rpp) * run;
+                rs = u_slot; ridx = q * run; run_left = run;
                 if (F.mode == 0) {
-                    const int px = blk_x0 + pj % blk_w, py = blk_y0 + pj / blk_w;
+                    const int ly = blk_w == 8 ? (pj >> 3) : pj / blk_w;
+                    px = blk_x0 + (pj - ly * blk_w); py = blk_y0 + ly;
                     sampleIndex = ((unsigned long long)py * (unsigned)F.gw + (unsigned)px) * (unsigned)spp + (unsigned)sj;
-                    ray = primaryRay<R, FEAT>(F, px, py, sj, sampleIndex);
                 } else {
                     sampleIndex = (unsigned long long)blk_slot0 + (unsigned)pj;
-                    const double* q = F.rays + 6 * sampleIndex;
-                    ray.o = mk<R>((R)__ldg(q), (R)__ldg(q + 1), (R)__ldg(q + 2));
-                    ray.d = mk<R>((R)__ldg(q + 3), (R)__ldg(q + 4), (R)__ldg(q + 5));
                 }
-                phase = PH_NEAREST; depth = 0; limit = F.recursion_limit; weight = R(1);
-                scol = mk<R>(R(0), R(0), R(0));
-                cn.add(ST_PRIMARY);
+                phase = PH_START;
                 need = false;
             }
             u_pos += min(__popc(m), avail);
             m = __ballot_sync(full, need);
+        }
+        if (phase == PH_START) {  // a new sample: dealt just now, or the next one of this lane's run
+            if (F.mode == 0) ray = primaryRay<R, FEAT>(F, px, py, sj, sampleIndex);
+            else {
+                const double* q = F.rays + 6 * sampleIndex;
+                ray.o = mk<R>((R)__ldg(q), (R)__ldg(q + 1), (R)__ldg(q + 2));
+                ray.d = mk<R>((R)__ldg(q + 3), (R)__ldg(q + 4), (R)__ldg(q + 5));
+            }
+            phase = PH_NEAREST; depth = 0; limit = F.recursion_limit; weight = R(1);
+            scol = mk<R>(R(0), R(0), R(0));
+            cn.add(ST_PRIMARY);
         }
         if (!__any_sync(full, phase != PH_IDLE)) break;
         if (phase == PH_IDLE) continue;
@@ -992,7 +1031,13 @@ __global__ void __launch_bounds__(kBlockThreads, FTB_MIN_BLOCKS) render_kernel(c
                 if (F.dbg_sub) F.dbg_sub[sampleIndex] = sub;
                 if (F.dbg_t) F.dbg_t[sampleIndex] = h.leaf >= 0 ? (double)h.t : -1.0;
             }
-            if (h.leaf < 0 || S.n_lights <= 0) { phase = PH_IDLE; retire = true; continue; }  // miss: empty sum (Shading.fs:137-139)
+            if (h.leaf < 0 || S.n_lights <= 0) {  // miss: empty sum (Shading.fs:137-139)
+                R* c = &ring_col[wib][rs][3 * ridx];
+                c[0] = scol.x; c[1] = scol.y; c[2] = scol.z;
+                retire = true;
+                if (--run_left > 0) { ++ridx; ++sj; ++sampleIndex; phase = PH_START; } else phase = PH_IDLE;
+                continue;
+            }
             cn.add(ST_SHADED);
             f = finalise<R, FEAT>(S, tr, h);
             local = mk<R>(R(0), R(0), R(0));
@@ -1060,8 +1105,11 @@ __global__ void __launch_bounds__(kBlockThreads, FTB_MIN_BLOCKS) render_kernel(c
             --limit; ++depth;
             phase = PH_NEAREST;
             cn.add(ST_REFLECTION);
-        } else {
-            phase = PH_IDLE; retire = true;
+        } else {  // the sample is complete: park its colour in the unit's slot; take the next sample of the run, if any
+            R* c = &ring_col[wib][rs][3 * ridx];
+            c[0] = scol.x; c[1] = scol.y; c[2] = scol.z;
+            retire = true;
+            if (--run_left > 0) { ++ridx; ++sj; ++sampleIndex; phase = PH_START; } else phase = PH_IDLE;
         }
     }
     if (overflow) atomicExch(F.overflow, 1u);
@@ -1089,7 +1137,7 @@ cudaError_t launch_render_impl(const DevScene<R>& s, const DevFrame<R>& f, bool 
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     // persistent grid: a multiple of the SM count, never more warps than there are work units to hand out
-    const long long units = f.mode == 0 ? (long long)f.n_local_tiles * 8 : (f.n_rays + 31) / 32;
+    const long long units = f.n_blocks;
     long long want = (long long)sm_count * per_sm;
     long long cap = (units + (kBlockThreads / 32) - 1) / (kBlockThreads / 32);
     int grid = (int)(want < cap ? want : cap);
