@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <memory>
 #include <string>
@@ -48,10 +49,10 @@ __device__ __forceinline__ unsigned char toByte(R c)
 // Tile-major shard buffers -> row-major frame.  corner = 1: CornerSampling.blendPixels
 // (Image.fs:134-144): pixel = average of the sample grid's [TL; TR; BL; BR] corners.
 template <typename R>
-__global__ void assemble_kernel(TilePtrs bufs, int shard_count, int tiles_x, int W, int H, int corner, int out_format, void* out)
+__global__ void assemble_kernel(TilePtrs bufs, int shard_count, int tiles_x, int W, int y0, int y1, int corner, int out_format, void* out)
 {
-    const long long n = (long long)W * H;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long n = (long long)W * y1;
+    for (long long i = (long long)W * y0 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const int x = (int)(i % W), y = (int)(i / W);
         R r, g, b;
         if (!corner) {
@@ -177,6 +178,7 @@ struct SceneStorage {
 
 struct PerDevice;
 template <typename R> SceneStorage<R>& storageOf(PerDevice* pd);
+typedef std::function<int(int)> ChunkDone;  // called after the launches of chunk k have been queued
 
 struct PerDevice {
     int device = -1;
@@ -186,6 +188,9 @@ struct PerDevice {
     cudaStream_t stream = nullptr;  // owned; used by the host-buffer entry points
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, done = nullptr;
     DevBuf control, jitter, tiles, out, dbg_prim, dbg_sub, dbg_t, rays, order;
+    std::vector<int> chunk_first;          // first position in the tile order of every chunk (+ end)
+    cudaStream_t copy_stream = nullptr;    // D2H of finished bands while later bands render
+    std::vector<cudaEvent_t> band_events;
     std::vector<unsigned char> order_key;  // what the cached tile order was computed for
     bool order_valid = false;
     std::vector<DevBuf> peer_tiles;  // on the gather device: one per remote shard
@@ -339,6 +344,7 @@ int getDevice(ftb_scene* sc, int device, PerDevice** out)
         CK(cudaSetDevice(device));
         CK(cudaDeviceGetAttribute(&pd->sm_count, cudaDevAttrMultiProcessorCount, device));
         CK(cudaStreamCreateWithFlags(&pd->stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&pd->copy_stream, cudaStreamNonBlocking));
         CK(cudaEventCreate(&pd->ev0));
         CK(cudaEventCreate(&pd->ev1));
         CK(cudaEventCreateWithFlags(&pd->done, cudaEventDisableTiming));
@@ -442,7 +448,8 @@ void fillStats(const Control& h, const ftb_scene& sc, ftb_stats* s)
 // causes (CSG programs, reflective surfaces spawn up to recursion_limit more generations) - puts the costly
 // tiles first, so the tail consists of cheap ones.  Ordering cannot change any pixel: tiles are independent.
 // Returns false when every tile has the same estimate (no order needed).
-bool computeTileOrder(const ftb_scene& sc, const ftb_camera& c, const ftb_render_params& p, const FrameGeom& g, std::vector<int>& order)
+bool computeTileOrder(const ftb_scene& sc, const ftb_camera& c, const ftb_render_params& p, const FrameGeom& g, int n_chunks, std::vector<int>& order,
+                      std::vector<int>& chunk_first)
 {
     const double kPiHalf = 1.5707963267948966;
     V3 o = {c.o[0], c.o[1], c.o[2]}, la = {c.look_at[0], c.look_at[1], c.look_at[2]}, up = {c.up[0], c.up[1], c.up[2]};
@@ -494,11 +501,19 @@ bool computeTileOrder(const ftb_scene& sc, const ftb_camera& c, const ftb_render
             for (int tx = tx0; tx <= tx1; ++tx) cost[(size_t)ty * g.tiles_x + tx] += (float)w;
         any = true;
     }
-    if (!any) return false;
+    // chunks = bands of tile rows (only used unsharded): chunk k holds tile rows [k ty / n, (k + 1) ty / n)
+    auto chunkOf = [&](int l) { return n_chunks <= 1 ? 0 : (int)(((long long)((l * g.shard_count + g.shard_index) / g.tiles_x) * n_chunks) / g.tiles_y); };
+    chunk_first.assign((size_t)n_chunks + 1, 0);
+    for (int l = 0; l < g.n_local_tiles; ++l) chunk_first[(size_t)chunkOf(l) + 1]++;
+    for (int k = 0; k < n_chunks; ++k) chunk_first[(size_t)k + 1] += chunk_first[(size_t)k];
+    if (!any && n_chunks <= 1) return false;
     order.resize((size_t)g.n_local_tiles);
     for (int l = 0; l < g.n_local_tiles; ++l) order[l] = l;
     auto costOf = [&](int l) { return cost[(size_t)l * g.shard_count + g.shard_index]; };
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return costOf(a) > costOf(b); });
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+        const int ca = chunkOf(a), cb = chunkOf(b);
+        return ca != cb ? ca < cb : costOf(a) > costOf(b);
+    });
     return true;
 }
 
@@ -506,7 +521,7 @@ bool computeTileOrder(const ftb_scene& sc, const ftb_camera& c, const ftb_render
 // `stream`; nothing here synchronises unless stats are requested.
 template <typename R>
 int launchFrame(ftb_scene* sc, PerDevice* pd, const ftb_camera* cam, const ftb_render_params* p, const FrameGeom& g, void* d_tiles,
-                const ftb_debug_out* d_dbg, ftb_stats* stats, cudaStream_t stream, bool timeKernel)
+                const ftb_debug_out* d_dbg, ftb_stats* stats, cudaStream_t stream, bool timeKernel, int n_chunks, const ChunkDone* chunkDone)
 {
     SceneStorage<R>& st = storageOf<R>(pd);
     if (!st.ready) { int rc = uploadScene<R>(*sc, st); if (rc != FTB_OK) return rc; }
@@ -536,13 +551,13 @@ int launchFrame(ftb_scene* sc, PerDevice* pd, const ftb_camera* cam, const ftb_r
     F.out = static_cast<R*>(d_tiles);
     if (d_dbg) { F.dbg_prim = d_dbg->prim_id; F.dbg_sub = d_dbg->sub_id; F.dbg_t = d_dbg->t; }
     {  // tile order: cached per (camera, frame geometry, recursion limit); recomputed + uploaded only when they change
-        std::vector<unsigned char> key(sizeof(ftb_camera) + 6 * sizeof(int));
+        std::vector<unsigned char> key(sizeof(ftb_camera) + 7 * sizeof(int));
         std::memcpy(key.data(), cam, sizeof(ftb_camera));
-        const int kk[6] = {p->width, p->height, p->sampling, g.shard_index, g.shard_count, p->recursion_limit};
+        const int kk[7] = {p->width, p->height, p->sampling, g.shard_index, g.shard_count, p->recursion_limit, n_chunks};
         std::memcpy(key.data() + sizeof(ftb_camera), kk, sizeof(kk));
         if (key != pd->order_key) {
             std::vector<int> order;
-            pd->order_valid = computeTileOrder(*sc, *cam, *p, g, order);
+            pd->order_valid = computeTileOrder(*sc, *cam, *p, g, n_chunks, order, pd->chunk_first);
             if (pd->order_valid) {
                 CK(pd->order.reserve(order.size() * sizeof(int)));
                 CK(cudaMemcpyAsync(pd->order.p, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
@@ -551,8 +566,9 @@ int launchFrame(ftb_scene* sc, PerDevice* pd, const ftb_camera* cam, const ftb_r
             pd->order_key.swap(key);
         }
         static const bool noOrder = std::getenv("FTB_NO_TILE_ORDER") != nullptr;  // A/B switch for measurements
-        F.tile_order = (pd->order_valid && !noOrder) ? static_cast<const int*>(pd->order.p) : nullptr;
+        F.tile_order = (pd->order_valid && (!noOrder || n_chunks > 1)) ? static_cast<const int*>(pd->order.p) : nullptr;
     }
+    const int* orderBase = F.tile_order;
     Control* ctl = static_cast<Control*>(pd->control.p);
     F.tile_counter = &ctl->tile_counter; F.overflow = &ctl->overflow; F.stats = ctl->stats;
     const bool wantStats = stats && p->collect_stats;
@@ -566,28 +582,34 @@ int launchFrame(ftb_scene* sc, PerDevice* pd, const ftb_camera* cam, const ftb_r
     // block is the indivisible quantum of the tail, so it shrinks (32 = 8x4 ... 1 pixel) until there are >= 24 blocks
     // per resident warp, but never below one warp-round of samples per block (and big frames keep big blocks, which
     // also bounds the number of atomics on the queue counter).
-    {
-        const long long warps = (long long)pd->sm_count * 5 * (kBlockThreads / 32);
-        const long long pixels = (long long)g.n_local_tiles * FTB_TILE_PIXELS;
-        int ppb = 32;
-        while (ppb > 1 && pixels / ppb < 24 * warps && (long long)(ppb / 2) * g.spp >= 32) ppb /= 2;
-        int bw = ppb >= 8 ? 8 : ppb, bh = ppb / bw;
-        F.bw_log = bw == 8 ? 3 : (bw == 4 ? 2 : (bw == 2 ? 1 : 0));
-        F.bh_log = bh == 4 ? 2 : (bh == 2 ? 1 : 0);
-        F.n_blocks = g.n_local_tiles * (FTB_TILE_PIXELS / ppb);
-    }
-    for (int s_base = 0; s_base < g.spp; s_base += UnitCap<R>::value) {
-        F.s_base = s_base;
-        F.s_count = std::min(UnitCap<R>::value, g.spp - s_base);
-        // run length: cheap samples amortise the dealing over up to 8 consecutive samples of a pixel, as long as
-        // every pixel still splits into >= 8 runs (the chain a lane can be stuck with stays 1/8 of a pixel)
-        int run = 1;
-        while (run < 8 && F.s_count % (run * 2) == 0 && F.s_count / (run * 2) >= 8) run *= 2;
-        F.run = run;
-        const unsigned rpp = (unsigned)(F.s_count / run);
-        F.rpp_magic = rpp <= 1 ? 0u : (unsigned)((1ull << 32) / rpp) + 1u;
-        if (s_base > 0) CK(cudaMemsetAsync(&ctl->tile_counter, 0, sizeof(unsigned int), stream));
-        CK(var->launch(st.view, F, wantStats, pd->sm_count, stream, &launches));
+    for (int chunk = 0; chunk < n_chunks; ++chunk) {
+        const int first = n_chunks > 1 ? pd->chunk_first[(size_t)chunk] : 0;
+        const int ntile = n_chunks > 1 ? pd->chunk_first[(size_t)chunk + 1] - first : g.n_local_tiles;
+        if (ntile > 0) {
+            F.tile_order = orderBase ? orderBase + first : nullptr;
+            const long long warps = (long long)pd->sm_count * 5 * (kBlockThreads / 32);
+            const long long pixels = (long long)ntile * FTB_TILE_PIXELS;
+            int ppb = 32;
+            while (ppb > 1 && pixels / ppb < 24 * warps && (long long)(ppb / 2) * g.spp >= 32) ppb /= 2;
+            int bw = ppb >= 8 ? 8 : ppb, bh = ppb / bw;
+            F.bw_log = bw == 8 ? 3 : (bw == 4 ? 2 : (bw == 2 ? 1 : 0));
+            F.bh_log = bh == 4 ? 2 : (bh == 2 ? 1 : 0);
+            F.n_blocks = ntile * (FTB_TILE_PIXELS / ppb);
+            for (int s_base = 0; s_base < g.spp; s_base += UnitCap<R>::value) {
+                F.s_base = s_base;
+                F.s_count = std::min(UnitCap<R>::value, g.spp - s_base);
+                // run length: cheap samples amortise the dealing over up to 8 consecutive samples of a pixel, as long as
+                // every pixel still splits into >= 8 runs (the chain a lane can be stuck with stays 1/8 of a pixel)
+                int run = 1;
+                while (run < 8 && F.s_count % (run * 2) == 0 && F.s_count / (run * 2) >= 8) run *= 2;
+                F.run = run;
+                const unsigned rpp = (unsigned)(F.s_count / run);
+                F.rpp_magic = rpp <= 1 ? 0u : (unsigned)((1ull << 32) / rpp) + 1u;
+                if (s_base > 0 || chunk > 0) CK(cudaMemsetAsync(&ctl->tile_counter, 0, sizeof(unsigned int), stream));
+                CK(var->launch(st.view, F, wantStats, pd->sm_count, stream, &launches));
+            }
+        }
+        if (chunkDone) { int rc = (*chunkDone)(chunk); if (rc != FTB_OK) return rc; }
     }
     if (timeKernel) CK(cudaEventRecord(pd->ev1, stream));
     if (stats) stats->kernel_launches += launches + 1;  // + the control-block memset
@@ -595,10 +617,10 @@ int launchFrame(ftb_scene* sc, PerDevice* pd, const ftb_camera* cam, const ftb_r
 }
 
 int launchFrameAny(ftb_scene* sc, PerDevice* pd, const ftb_camera* cam, const ftb_render_params* p, const FrameGeom& g, void* d_tiles,
-                   const ftb_debug_out* d_dbg, ftb_stats* stats, cudaStream_t stream, bool timeKernel)
+                   const ftb_debug_out* d_dbg, ftb_stats* stats, cudaStream_t stream, bool timeKernel, int n_chunks = 1, const ChunkDone* chunkDone = nullptr)
 {
-    if (p->precision == FTB_PRECISION_FP64_VERIFY) return launchFrame<double>(sc, pd, cam, p, g, d_tiles, d_dbg, stats, stream, timeKernel);
-    return launchFrame<float>(sc, pd, cam, p, g, d_tiles, d_dbg, stats, stream, timeKernel);
+    if (p->precision == FTB_PRECISION_FP64_VERIFY) return launchFrame<double>(sc, pd, cam, p, g, d_tiles, d_dbg, stats, stream, timeKernel, n_chunks, chunkDone);
+    return launchFrame<float>(sc, pd, cam, p, g, d_tiles, d_dbg, stats, stream, timeKernel, n_chunks, chunkDone);
 }
 
 // Reads the control block back (synchronises the stream) and folds it into stats.
@@ -616,17 +638,19 @@ int finishStats(ftb_scene* sc, PerDevice* pd, ftb_stats* stats, cudaStream_t str
     return FTB_OK;
 }
 
-int launchAssemble(const ftb_render_params* p, const FrameGeom& g, const void* const* bufs, void* d_out, cudaStream_t stream)
+int launchAssemble(const ftb_render_params* p, const FrameGeom& g, const void* const* bufs, void* d_out, cudaStream_t stream, int y0 = 0, int y1 = -1)
 {
     TilePtrs tp;
     std::memset(&tp, 0, sizeof(tp));
     for (int i = 0; i < g.shard_count; ++i) tp.p[i] = bufs[i];
-    const long long n = (long long)p->width * p->height;
+    if (y1 < 0) y1 = p->height;
+    const long long n = (long long)p->width * (y1 - y0);
+    if (n <= 0) return FTB_OK;
     int grid = (int)std::min<long long>((n + 255) / 256, 148 * 16);
     if (p->precision == FTB_PRECISION_FP64_VERIFY)
-        assemble_kernel<double><<<grid, 256, 0, stream>>>(tp, g.shard_count, g.tiles_x, p->width, p->height, g.corner ? 1 : 0, p->out_format, d_out);
+        assemble_kernel<double><<<grid, 256, 0, stream>>>(tp, g.shard_count, g.tiles_x, p->width, y0, y1, g.corner ? 1 : 0, p->out_format, d_out);
     else
-        assemble_kernel<float><<<grid, 256, 0, stream>>>(tp, g.shard_count, g.tiles_x, p->width, p->height, g.corner ? 1 : 0, p->out_format, d_out);
+        assemble_kernel<float><<<grid, 256, 0, stream>>>(tp, g.shard_count, g.tiles_x, p->width, y0, y1, g.corner ? 1 : 0, p->out_format, d_out);
     CK(cudaGetLastError());
     return FTB_OK;
 }
@@ -715,6 +739,8 @@ void ftb_scene_destroy(ftb_scene* sc)
         if (pd->ev1) cudaEventDestroy(pd->ev1);
         if (pd->done) cudaEventDestroy(pd->done);
         if (pd->stream) cudaStreamDestroy(pd->stream);
+        if (pd->copy_stream) cudaStreamDestroy(pd->copy_stream);
+        for (cudaEvent_t e : pd->band_events) cudaEventDestroy(e);
     }
     delete sc;
 }
@@ -781,6 +807,41 @@ int ftb_render(ftb_scene* scene, const ftb_camera* camera, const ftb_render_para
         return fail(FTB_ERR_BAD_ARG, "ftb_render renders whole frames; use ftb_render_tiles_device for one shard");
     }
     const size_t rs = realSize(p.precision);
+    // ---- one GPU, plain frame: render in bands of tile rows and copy each finished band to the host while the
+    // next one renders (the D2H of a 1080p f64 frame takes half as long as rendering it) ------------------------------
+    static const bool noBands = std::getenv("FTB_NO_BANDS") != nullptr;  // A/B switch for measurements
+    if (n_gpus == 1 && !dbg && !stats && !full.corner && !noBands && (long long)p.width * p.height >= 262144 && full.tiles_y >= 8) {
+        const int kBands = 4;
+        PerDevice* pd = nullptr;
+        if ((rc = getDevice(scene, restore.dev, &pd)) != FTB_OK) return rc;
+        CK(pd->tiles.reserve((size_t)full.n_local_tiles * FTB_TILE_PIXELS * 3 * rs));
+        CK(pd->out.reserve(outBytes(&p)));
+        while ((int)pd->band_events.size() < kBands) {
+            cudaEvent_t e;
+            CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            pd->band_events.push_back(e);
+        }
+        const size_t rowBytes = outBytes(&p) / (size_t)p.height;
+        const void* buf0 = pd->tiles.p;
+        ChunkDone bandDone = [&](int c) -> int {
+            const int r0 = (c * full.tiles_y + kBands - 1) / kBands, r1 = ((c + 1) * full.tiles_y + kBands - 1) / kBands;
+            const int y0 = std::min(p.height, r0 * FTB_TILE_H), y1 = std::min(p.height, r1 * FTB_TILE_H);
+            if (y1 <= y0) return FTB_OK;
+            int rc2 = launchAssemble(&p, full, &buf0, pd->out.p, pd->stream, y0, y1);
+            if (rc2 != FTB_OK) return rc2;
+            CK(cudaEventRecord(pd->band_events[c], pd->stream));
+            CK(cudaStreamWaitEvent(pd->copy_stream, pd->band_events[c], 0));
+            CK(cudaMemcpyAsync(static_cast<char*>(out) + (size_t)y0 * rowBytes, static_cast<const char*>(pd->out.p) + (size_t)y0 * rowBytes,
+                               (size_t)(y1 - y0) * rowBytes, cudaMemcpyDeviceToHost, pd->copy_stream));
+            return FTB_OK;
+        };
+        if ((rc = launchFrameAny(scene, pd, camera, &p, full, pd->tiles.p, nullptr, nullptr, pd->stream, false, kBands, &bandDone)) != FTB_OK) return rc;
+        bool overflow = false;
+        if ((rc = finishStats(scene, pd, nullptr, pd->stream, false, &overflow)) != FTB_OK) return rc;
+        CK(cudaStreamSynchronize(pd->copy_stream));
+        if (overflow) return fail(FTB_ERR_HIT_OVERFLOW, "a CSG operand produced more than 32 crossings on one ray");
+        return FTB_OK;
+    }
     std::vector<PerDevice*> pds(n_gpus);
     std::vector<const void*> bufs(n_gpus);
     const int primary = n_gpus > 1 ? 0 : restore.dev;

@@ -38,6 +38,10 @@ namespace ftb {
 #define FTB_DEV __device__ __forceinline__
 
 // ---- scalar helpers -------------------------------------------------------------------------------
+FTB_DEV float min_(float a, float b) { return fminf(a, b); }
+FTB_DEV double min_(double a, double b) { return fmin(a, b); }
+FTB_DEV float max_(float a, float b) { return fmaxf(a, b); }
+FTB_DEV double max_(double a, double b) { return fmax(a, b); }
 FTB_DEV float sqrt_(float x) { return sqrtf(x); }
 FTB_DEV double sqrt_(double x) { return sqrt(x); }
 FTB_DEV float abs_(float x) { return fabsf(x); }
@@ -126,8 +130,16 @@ FTB_DEV Vec<R> normalise(Vec<R> v)  // CommonTypes.fs:63-67
 }
 template <typename R>
 FTB_DEV Vec<R> reflect(Vec<R> n, Vec<R> v) { return v - (R(2) * dot(v, n)) * n; }  // :72
+// CommonTypes.fs:74-75.  In FP32 the dot product of two normalised vectors exceeds 1 by an ulp whenever the angle is
+// below ~3e-4 rad and acos would poison the pixel with NaN; in the reference's doubles that needs an angle below
+// ~1e-8 rad, i.e. it does not happen.  The product build clamps, the verification build stays literal.
 template <typename R>
-FTB_DEV R angleBetween(Vec<R> a, Vec<R> b) { return acos_(dot(normalise(a), normalise(b))); }  // :74-75
+FTB_DEV R angleBetween(Vec<R> a, Vec<R> b)
+{
+    R c = dot(normalise(a), normalise(b));
+    if constexpr (sizeof(R) == 4) c = min_(R(1), max_(R(-1), c));
+    return acos_(c);
+}
 template <typename R>
 FTB_DEV Vec<R> perpendicularComponent(Vec<R> a, Vec<R> b) { Vec<R> na = normalise(a); return b - dot(b, na) * na; }  // :77-79
 
@@ -264,10 +276,6 @@ FTB_DEV bool triangleT(const typename V4<R>::type* rows, const Ray<R>& ray, R& t
     return t > epsilon;
 }
 
-FTB_DEV float min_(float a, float b) { return fminf(a, b); }
-FTB_DEV double min_(double a, double b) { return fmin(a, b); }
-FTB_DEV float max_(float a, float b) { return fmaxf(a, b); }
-FTB_DEV double max_(double a, double b) { return fmax(a, b); }
 
 // Ray vs. one child box of a BVH node: entry distance, or +inf when the box cannot hold a hit with
 // 0 <= t <= tmax.  fmin / fmax drop the NaNs that 0 * inf produces for rays parallel to a slab; the exit

@@ -220,3 +220,25 @@ def test_sample_counts_and_multi_pass_blend(spp, prec):
     check(ref, got, prec, "house-spp%d" % spp)
     if prec == abi.PRECISION_FP64_VERIFY:
         assert np.abs(got["rgb"] - ref["rgb"]).max() < 1e-9
+
+
+def test_banded_host_render_matches_device_path():
+    """ftb_render overlaps the D2H copy of finished bands of tile rows with the rendering of later bands (frames
+    of >= 512x512).  Bands, tile order and queue block size only change WHEN a sample is traced, never its
+    value: the host frame equals the frame assembled from one un-banded device launch, bit for bit."""
+    import torch
+    W, H, spp = 640, 528, 2
+    sc = parse(scenes.night_house(res=(W, H), spp=spp))
+    jit = frontend.jitter_pattern(3, spp)
+    with api.Scene(sc) as scene:
+        host = scene.render(W, H, spp, jit, out_format=abi.OUT_RGB_F32)["rgb"]
+        p = api.make_params(W, H, spp, jit, out_format=abi.OUT_RGB_F32)
+        buf = torch.empty(api.tile_buffer_bytes(p), dtype=torch.uint8, device="cuda")
+        s = torch.cuda.current_stream().cuda_stream
+        scene.render_tiles_device(p, buf.data_ptr(), stream=s)
+        out = torch.empty((H, W, 3), dtype=torch.float32, device="cuda")
+        api.assemble_device(p, [buf.data_ptr()], out.data_ptr(), stream=s)
+        torch.cuda.synchronize()
+        again = scene.render(W, H, spp, jit, out_format=abi.OUT_RGB_F32)["rgb"]
+    assert (out.cpu().numpy() == host).all()
+    assert (again == host).all()
