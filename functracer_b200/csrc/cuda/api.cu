@@ -252,9 +252,10 @@ int uploadScene(const ftb_scene& sc, SceneStorage<R>& st)
         v.n_leaves = (int)L.leaves.size();
     }
     {
-        std::vector<int4> items; std::vector<R4> bounds; std::vector<int2> ops;
+        std::vector<int4> items; std::vector<R4> bounds; std::vector<int2> ops, progs;
         for (const Item& it : L.items) {
             items.push_back(make_int4(it.kind, it.a, it.b, it.casts_shadow));
+            progs.push_back(make_int2(it.prog_first, it.prog_count));
             // conservative: radius inflated by 0.2 % + 1e-5 so that FP32 rounding of the test cannot cull a true hit
             const double ri = it.bound_r < 0 ? -1.0 : it.bound_r * 1.002 + 1e-5;
             bounds.push_back(Mk4<R>::make(it.bound_c[0], it.bound_c[1], it.bound_c[2], ri < 0 ? -1.0 : ri * ri));
@@ -263,7 +264,7 @@ int uploadScene(const ftb_scene& sc, SceneStorage<R>& st)
         std::vector<unsigned> casts((L.items.size() + 31) / 32 + 1, 0u);
         for (size_t i = 0; i < L.items.size(); ++i)
             if (L.items[i].casts_shadow) casts[i >> 5] |= 1u << (i & 31);
-        UP(items, v.items) UP(bounds, v.item_bound) UP(ops, v.ops) UP(casts, v.item_casts)
+        UP(items, v.items) UP(bounds, v.item_bound) UP(ops, v.ops) UP(casts, v.item_casts) UP(progs, v.item_prog)
         v.n_items = (int)L.items.size();
     }
     {
@@ -483,7 +484,7 @@ bool computeTileOrder(const ftb_scene& sc, const ftb_camera& c, const ftb_render
         if (it.kind == ITEM_LEAF) leafWork(it.a);
         else {
             w = 0.0;
-            for (int q = it.a; q < it.a + it.b; ++q)
+            for (int q = it.prog_first; q < it.prog_first + it.prog_count; ++q)
                 if (sc.L.ops[q].kind == OP_LEAF) { leafWork(sc.L.ops[q].arg); w += 2.0; }
         }
         w *= (1.0 + (double)sc.lights.size());                              // a shaded hit adds one shadow ray per light

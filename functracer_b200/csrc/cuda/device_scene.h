@@ -33,11 +33,12 @@ enum Feature : unsigned {
     FT_CUBE = 0x01,   // LEAF_CUBE
     FT_ROUND = 0x02,  // LEAF_SQUARE, LEAF_CIRCLE, LEAF_CYLINDER, LEAF_CONE
     FT_MESH = 0x04,   // LEAF_TRIANGLE, LEAF_MESH (BSP traversal)
-    FT_CSG = 0x08,    // CSG programs
+    FT_CSG = 0x08,    // CSG items that are a binary op of two single leaves (evaluated in registers)
     FT_TEX = 0x10,    // grid / image textures, sphere uv
     FT_ROUGH = 0x20,  // Oren-Nayar diffuse
     FT_RNG = 0x40,    // soft directional lights, depth of field
-    FT_ALL = 0x7f
+    FT_CSGN = 0x80,   // any other CSG item (general post-order program, inlined)
+    FT_ALL = 0xff
 };
 
 enum StatSlot : int {
@@ -62,7 +63,8 @@ struct DevScene {
     const int4* leaf_meta;  // x = kind | identity << 8, y = surface, z = prim, w = payload
     int n_leaves;
     // top-level items in enumeration order
-    const int4* items;     // x = kind, y = a, z = b, w = casts_shadow
+    const int4* items;     // x = kind (| op << 8 for ITEM_CSG2), y = a, z = b, w = casts_shadow
+    const int2* item_prog; // CSG items: x = first op, y = op count of the general program
     const R4* item_bound;  // xyz = centre, w = (inflated radius)^2 of a conservative bounding sphere (< 0 unbounded)
     const unsigned* item_casts;  // bit j of word w: item 32 w + j can block light (something under it has applyLighting)
     int n_items;

@@ -410,7 +410,14 @@ struct Lowerer {
             Sphere b; bool e = true; int lists = 0; bool casts = false;
             if (!emitProgram(node, cx, depth, b, e, lists, casts)) return false;
             L.max_csg_lists = std::max(L.max_csg_lists, lists);
-            pushItem(ITEM_CSG, first, (int)L.ops.size() - first, casts, b, e);
+            const int count = (int)L.ops.size() - first;
+            pushItem(ITEM_CSG, first, count, casts, b, e);
+            L.items.back().prog_first = first; L.items.back().prog_count = count;
+            if (count == 3 && L.ops[first].kind == OP_LEAF && L.ops[first + 1].kind == OP_LEAF && L.ops[first + 2].kind >= OP_UNION) {
+                Item& it = L.items.back();
+                it.kind = ITEM_CSG2 | (L.ops[first + 2].kind << 8);
+                it.a = L.ops[first].arg; it.b = L.ops[first + 1].arg;
+            }
             return true;
         }
         default: return fail(FTB_ERR_BAD_SCENE, "bad node kind");
@@ -606,7 +613,10 @@ int lower_scene(const ftb_scene_desc& d, Lowered& out, std::string& err)
         if (lf.kind == LEAF_SQUARE || lf.kind == LEAF_CIRCLE || lf.kind == LEAF_CYLINDER || lf.kind == LEAF_CONE) f |= 0x02;
         if (lf.kind == LEAF_TRIANGLE || lf.kind == LEAF_MESH) f |= 0x04;
     }
-    if (out.has_csg) f |= 0x08;
+    for (const Item& it : out.items) {
+        if ((it.kind & 0xff) == ITEM_CSG2) f |= 0x08;  // a two-leaf CSG pair
+        if (it.kind == ITEM_CSG) f |= 0x80;            // a general CSG program
+    }
     if (out.has_texture) f |= 0x10;
     if (out.has_rough) f |= 0x20;
     if (out.has_soft_light) f |= 0x40;

@@ -34,7 +34,10 @@ enum LeafKind : int32_t {
     LEAF_MESH = 8
 };
 
-enum ItemKind : int32_t { ITEM_LEAF = 0, ITEM_CSG = 1 };
+// ITEM_CSG2: a CSG node whose two operands are single leaves (`subtract cube (scale .65 sphere)`): the device
+// evaluates it in registers when neither leaf yields more than two crossings; kind = ITEM_CSG2 | (CsgOpKind << 8),
+// a / b = the two leaves.  Every CSG item also keeps its general post-order program (prog_first / prog_count).
+enum ItemKind : int32_t { ITEM_LEAF = 0, ITEM_CSG = 1, ITEM_CSG2 = 2 };
 
 enum CsgOpKind : int32_t {
     OP_LEAF = 0,   // arg = leaf index: push its hit list
@@ -80,8 +83,9 @@ struct TexDef {
 
 struct Item {
     int32_t kind;
-    int32_t a;  // ITEM_LEAF: leaf index; ITEM_CSG: first op
-    int32_t b;  // ITEM_CSG: op count
+    int32_t a;  // ITEM_LEAF: leaf index; ITEM_CSG: first op;  ITEM_CSG2: leaf A
+    int32_t b;  // ITEM_CSG: op count;                          ITEM_CSG2: leaf B
+    int32_t prog_first, prog_count;  // CSG items: the post-order program
     int32_t casts_shadow;  // 0 = every leaf under it has applyLighting = false (Scene.fs:121)
     // conservative world-space bounding sphere of everything the item can report (radius < 0: unbounded)
     double bound_c[3];
@@ -125,7 +129,7 @@ struct Lowered {
     bool has_csg = false, has_mesh = false, has_texture = false, has_image = false;
     bool has_soft_light = false, has_rough = false, has_reflection = false;
     // Kernel features this scene needs, as device_scene.h `Feature` bits (cube 1, round 2, mesh 4, csg 8,
-    // texture 16, Oren-Nayar 32, rng 64); camera depth of field adds rng at render time.
+    // texture 16, Oren-Nayar 32, rng 64, general CSG 128); camera depth of field adds rng at render time.
     unsigned features = 0;
 };
 

@@ -563,6 +563,116 @@ FTB_DEV int evalCsg(const DevScene<R>& S, int opFirst, int opCount, const Ray<R>
     return sink.top;
 }
 
+// A nearest/any query against one CSG item through the general program.  Out of line: it is the rare path for
+// two-leaf items and keeps the per-ray hit stack (local memory) out of the hot loop's code.  Everything crosses the
+// call by value so that the caller's sink and ray stay in registers.
+template <typename R>
+struct CsgAnswer {
+    R t;
+    int leaf, sub, flip;  // leaf < 0: the item offers nothing that beats `limit`
+    bool overflow;
+};
+template <typename R, unsigned FEAT, bool STATS>
+__device__ __noinline__ CsgAnswer<R> csgGeneral(const DevScene<R>* S, int opFirst, int opCount, Ray<R> wr, R limit, bool any, Counters<STATS>* cnp)
+{
+    Counters<STATS> scratch;
+    Counters<STATS>& cn = cnp ? *cnp : scratch;
+    CsgAnswer<R> ans;
+    ans.t = limit; ans.leaf = -1; ans.sub = 0; ans.flip = 0; ans.overflow = false;
+    HitRec<R> stack[kHitCap];
+    const int nh = evalCsg<R, FEAT, STATS>(*S, opFirst, opCount, wr, stack, ans.overflow, cn);
+    for (int k = 0; k < nh; ++k) {  // sorted by t
+        const R ht = stack[k].t;
+        if (!(ht >= R(0))) continue;
+        if (!any) {  // the first t >= 0 is this item's candidate; it wins if it beats the best so far
+            if (ht < limit) {
+                ans.t = ht; ans.leaf = (int)(stack[k].id & kIdLeafMask); ans.sub = (int)((stack[k].id >> kIdSubShift) & 7u);
+                ans.flip = (stack[k].id & kIdFlip) ? 1 : 0;
+            }
+            break;
+        }
+        if (!(ht < limit)) break;
+        const int leaf = (int)(stack[k].id & kIdLeafMask);
+        if (__ldg(S->surf_i + __ldg(S->leaf_meta + leaf).y).z) { ans.leaf = leaf; break; }
+    }
+    return ans;
+}
+
+// <= 2 crossings of one leaf, in registers.
+template <typename R>
+struct PairSink {
+    static constexpr bool kIsRay = false;
+    R t0, t1;
+    int s0, s1, n;
+    FTB_DEV void hit(R ht, int hsub)
+    {
+        if (n == 0) { t0 = ht; s0 = hsub; } else if (n == 1) { t1 = ht; s1 = hsub; }
+        ++n;
+    }
+    FTB_DEV bool done() const { return false; }
+};
+
+// Csg.constructedSolid (Csg.fs:74-94) for two single-leaf operands with at most two crossings each (the common
+// case: convex leaves), entirely in registers: the same stable insertion sort over A's hits then B's, the same
+// toggling walk and rule tables as evalCsg, fused with the nearest / any selection.  Returns false (nothing
+// consumed) when a leaf reports more than two crossings; the caller then runs the general program.
+template <typename R, unsigned FEAT, bool STATS>
+FTB_DEV bool csgPair(const DevScene<R>& S, int leafA, int leafB, int op, const Ray<R>& wr, RaySink<R>& best, Counters<STATS>& cn)
+{
+    PairSink<R> a, b;
+    a.n = 0; a.t0 = a.t1 = R(0); a.s0 = a.s1 = 0;
+    b.n = 0; b.t0 = b.t1 = R(0); b.s0 = b.s1 = 0;
+    intersectLeaf<R, FEAT & ~FT_MESH, STATS>(S, leafA, wr, a, cn);
+    if (a.n > 2) return false;
+    intersectLeaf<R, FEAT & ~FT_MESH, STATS>(S, leafB, wr, b, cn);
+    if (b.n > 2) return false;
+    cn.add(ST_CSG_OPS);
+    R mt[4];
+    unsigned mid[4];
+    int mn = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { mt[i] = R(0); mid[i] = 0u; }
+    auto insert = [&](R t, unsigned id) {  // Seq.sortBy (stable): after every element that is not greater
+        int p = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) p += (i < mn && !(t < mt[i])) ? 1 : 0;
+#pragma unroll
+        for (int i = 3; i >= 1; --i) if (i > p && i <= mn) { mt[i] = mt[i - 1]; mid[i] = mid[i - 1]; }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) if (i == p) { mt[i] = t; mid[i] = id; }
+        ++mn;
+    };
+    if (a.n > 0) insert(a.t0, (unsigned)leafA | ((unsigned)(a.s0 & 7) << kIdSubShift));
+    if (a.n > 1) insert(a.t1, (unsigned)leafA | ((unsigned)(a.s1 & 7) << kIdSubShift));
+    if (b.n > 0) insert(b.t0, (unsigned)leafB | ((unsigned)(b.s0 & 7) << kIdSubShift) | kIdSideB);
+    if (b.n > 1) insert(b.t1, (unsigned)leafB | ((unsigned)(b.s1 & 7) << kIdSubShift) | kIdSideB);
+    const unsigned rules = csgRuleTable(op);
+    bool inA = false, inB = false, decided = false;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (k < mn && !decided) {
+            const unsigned id = mid[k];
+            const R ht = mt[k];
+            const bool hitB = (id & kIdSideB) != 0;
+            const unsigned rule = (rules >> (2 * ((hitB ? 4 : 0) + (inA ? 2 : 0) + (inB ? 1 : 0)))) & 3u;
+            if (hitB) inB = !inB; else inA = !inA;
+            if (rule != 1u && ht >= R(0)) {
+                const int leaf = (int)(id & kIdLeafMask);
+                if (!best.any) {  // the item's first crossing with t >= 0 is its candidate (Scene.closest)
+                    if (ht < best.limit) { best.limit = ht; best.leaf = leaf; best.sub = (int)((id >> kIdSubShift) & 7u); best.flip = rule == 2u ? 1 : 0; }
+                    decided = true;
+                } else if (!(ht < best.limit)) {
+                    decided = true;
+                } else if (__ldg(S.surf_i + __ldg(S.leaf_meta + leaf).y).z) {  // Scene.lightIsBocked: applyLighting surfaces only
+                    best.leaf = leaf;
+                    decided = true;
+                }
+            }
+        }
+    }
+    return true;
+}
+
 template <typename R>
 struct HitInfo {
     R t;
@@ -608,22 +718,38 @@ FTB_DEV HitInfo<R> traceScene(const DevScene<R>& S, const Ray<R>& wr, R limit, b
             if (item.x == ITEM_LEAF) {
                 best.cur = item.y;
                 intersectLeaf<R, FEAT, STATS>(S, item.y, wr, best, cn);
-            } else if constexpr ((FEAT & FT_CSG) != 0) {
-                HitRec<R> stack[kHitCap];
-                const int nh = evalCsg<R, FEAT, STATS>(S, item.y, item.z, wr, stack, overflow, cn);
-                for (int k = 0; k < nh; ++k) {  // sorted by t
-                    const R ht = stack[k].t;
-                    if (!(ht >= R(0))) continue;
-                    if (!any) {  // the first t >= 0 is this item's candidate; it wins if it beats best
-                        if (ht < best.limit) {
-                            best.limit = ht; best.leaf = (int)(stack[k].id & kIdLeafMask); best.sub = (int)((stack[k].id >> kIdSubShift) & 7u);
-                            best.flip = (stack[k].id & kIdFlip) ? 1 : 0;
+            } else if constexpr ((FEAT & (FT_CSG | FT_CSGN)) != 0) {
+                bool done = false;
+                if constexpr ((FEAT & FT_CSG) != 0) {
+                    if ((item.x & 0xff) == ITEM_CSG2) done = csgPair<R, FEAT, STATS>(S, item.y, item.z, item.x >> 8, wr, best, cn);
+                }
+                if (!done) {  // general program, or a leaf with more than two crossings
+                    const int2 prog = __ldg(S.item_prog + it);
+                    if constexpr ((FEAT & FT_CSGN) != 0) {  // scenes with general CSG items: inline (no call, no spills around it)
+                        HitRec<R> stack[kHitCap];
+                        const int nh = evalCsg<R, FEAT, STATS>(S, prog.x, prog.y, wr, stack, best.overflow, cn);
+                        for (int k = 0; k < nh; ++k) {  // sorted by t
+                            const R ht = stack[k].t;
+                            if (!(ht >= R(0))) continue;
+                            if (!any) {  // the first t >= 0 is this item's candidate; it wins if it beats best
+                                if (ht < best.limit) {
+                                    best.limit = ht; best.leaf = (int)(stack[k].id & kIdLeafMask); best.sub = (int)((stack[k].id >> kIdSubShift) & 7u);
+                                    best.flip = (stack[k].id & kIdFlip) ? 1 : 0;
+                                }
+                                break;
+                            }
+                            if (!(ht < best.limit)) break;
+                            const int leaf = (int)(stack[k].id & kIdLeafMask);
+                            if (__ldg(S.surf_i + __ldg(S.leaf_meta + leaf).y).z) { best.leaf = leaf; break; }
                         }
-                        break;
+                    } else {  // pair-only scenes: the rare fallback stays out of line, off the hot loop's instruction footprint
+                        const CsgAnswer<R> ans = csgGeneral<R, FEAT, STATS>(&S, prog.x, prog.y, wr, best.limit, any, STATS ? &cn : nullptr);
+                        if (ans.leaf >= 0) {
+                            best.leaf = ans.leaf;
+                            if (!any) { best.limit = ans.t; best.sub = ans.sub; best.flip = ans.flip; }
+                        }
+                        best.overflow = best.overflow || ans.overflow;
                     }
-                    if (!(ht < best.limit)) break;
-                    const int leaf = (int)(stack[k].id & kIdLeafMask);
-                    if (__ldg(S.surf_i + __ldg(S.leaf_meta + leaf).y).z) { best.leaf = leaf; break; }
                 }
             }
             if (any && best.leaf >= 0) cand = 0;
@@ -873,7 +999,7 @@ __device__ __noinline__ void foldUnit(const R* col, const int* hdr, R* out, int 
 }
 
 template <typename R, unsigned FEAT, bool STATS>
-__global__ void __launch_bounds__(kBlockThreads, FTB_MIN_BLOCKS) render_kernel(const DevScene<R> S, const DevFrame<R> F)
+__global__ void __launch_bounds__(kBlockThreads, FTB_MIN_BLOCKS) render_kernel(const __grid_constant__ DevScene<R> S, const __grid_constant__ DevFrame<R> F)
 {
     typedef typename V4<R>::type R4;
     constexpr int CAP = UnitCap<R>::value;
