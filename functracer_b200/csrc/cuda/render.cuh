@@ -688,7 +688,9 @@ FTB_DEV HitInfo<R> traceScene(const DevScene<R>& S, const Ray<R>& wr, R limit, b
     typedef typename V4<R>::type R4;
     RaySink<R> best;
     best.limit = limit; best.leaf = -1; best.sub = 0; best.flip = 0; best.any = any; best.cur = 0; best.overflow = false;
-    const R inv_dd = R(1) / dot(wr.d, wr.d);
+    // unit direction for the bound tests (their slack covers its rounding)
+    const R inv_len = R(1) / sqrt_(dot(wr.d, wr.d));
+    const Vec<R> du = mk<R>(wr.d.x * inv_len, wr.d.y * inv_len, wr.d.z * inv_len);
     for (int base = 0; base < S.n_items; base += 32) {
         // ---- phase A: which of the next 32 items can this ray's line touch at all?  Branch-free and unrolled:
         // the loads and the arithmetic of neighbouring items overlap (the serial per-item version spent a third
@@ -699,12 +701,11 @@ FTB_DEV HitInfo<R> traceScene(const DevScene<R>& S, const Ray<R>& wr, R limit, b
         for (int j = 0; j < n; ++j) {
             const R4 bound = ldg4<R>(S.item_bound + base + j);  // xyz = centre, w = inflated radius^2 (< 0: unbounded)
             const Vec<R> oc = mk<R>(bound.x - wr.o.x, bound.y - wr.o.y, bound.z - wr.o.z);
-            const R b = dot(oc, wr.d);
-            const R tc = b * inv_dd;
-            const Vec<R> l = mk<R>(oc.x - tc * wr.d.x, oc.y - tc * wr.d.y, oc.z - tc * wr.d.z);  // centre -> line, perpendicular
+            const R b = dot(oc, du);                                 // distance along the ray to the point nearest the centre
             const R oc2 = dot(oc, oc);
-            const bool miss = dot(l, l) > bound.w + R(1e-6) * oc2;  // the ray's line misses the bound: no crossing at all
-            const bool behind = b < R(0) && oc2 > bound.w;          // bound entirely behind the origin: every crossing has t < 0
+            // |centre - line|^2 = oc2 - b^2; the 1e-6 oc2 slack covers the cancellation (and the radius is inflated)
+            const bool miss = oc2 - b * b > bound.w + R(1e-6) * oc2;  // the ray's line misses the bound: no crossing at all
+            const bool behind = b < R(0) && oc2 > bound.w;            // bound entirely behind the origin: every crossing has t < 0
             const bool unbounded = bound.w < R(0);
             cn.add(ST_BOUND_TESTS, unbounded ? 0u : 1u);
             cand |= (unbounded || !(miss || behind)) ? (1u << j) : 0u;

@@ -242,3 +242,18 @@ def test_banded_host_render_matches_device_path():
         again = scene.render(W, H, spp, jit, out_format=abi.OUT_RGB_F32)["rgb"]
     assert (out.cpu().numpy() == host).all()
     assert (again == host).all()
+
+
+def test_in_process_multi_gpu_render_matches_single_gpu():
+    """ftb_render(n_gpus = 2): tiles dealt round-robin to two devices, each with its own atomic queue, shard 1's
+    tile buffer copied to device 0 with cudaMemcpyPeerAsync (NVLink), frame assembled there.  Same bits as one GPU."""
+    if api.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    W, H, spp = 320, 200, 2
+    sc = parse(scenes.hollow_sphere(res=(W, H), spp=spp))
+    jit = frontend.jitter_pattern(2, spp)
+    with api.Scene(sc) as scene:
+        one = scene.render(W, H, spp, jit, out_format=abi.OUT_RGB_F32)["rgb"]
+        two = scene.render(W, H, spp, jit, out_format=abi.OUT_RGB_F32, n_gpus=2, stats=True)
+    assert (two["rgb"] == one).all()
+    assert two["stats"].primary_rays == W * H * spp
