@@ -443,6 +443,23 @@ void fillStats(const Control& h, const ftb_scene& sc, ftb_stats* s)
     s->flops += f;
 }
 
+// Bands of tile rows for the host-buffer path: band k = tile rows [bandFirstRow(k), bandFirstRow(k + 1)).  The D2H copy
+// of band k overlaps the rendering of band k + 1, so only the LAST band's copy is exposed: the bands shrink towards
+// the end (30 / 30 / 25 / 15 % for four bands).
+inline int bandFirstRow(int k, int n, int tiles_y)
+{
+    if (k <= 0) return 0;
+    if (k >= n) return tiles_y;
+    if (n == 4) { static const double cum[5] = {0.0, 0.30, 0.60, 0.85, 1.0}; return (int)(cum[k] * tiles_y + 0.5); }
+    return (int)(((long long)k * tiles_y) / n);
+}
+inline int bandOfRow(int row, int n, int tiles_y)
+{
+    int k = 0;
+    while (k + 1 < n && row >= bandFirstRow(k + 1, n, tiles_y)) ++k;
+    return k;
+}
+
 // Longest-processing-time-first tile order.  The persistent kernel hands tiles out from an atomic queue; a lane
 // keeps its pixel for all samples and all bounce generations, so the last tiles handed out set the tail.  A
 // static estimate - the projected bounding spheres of the items, weighted by how much work a hit on them
@@ -502,8 +519,8 @@ bool computeTileOrder(const ftb_scene& sc, const ftb_camera& c, const ftb_render
             for (int tx = tx0; tx <= tx1; ++tx) cost[(size_t)ty * g.tiles_x + tx] += (float)w;
         any = true;
     }
-    // chunks = bands of tile rows (only used unsharded): chunk k holds tile rows [k ty / n, (k + 1) ty / n)
-    auto chunkOf = [&](int l) { return n_chunks <= 1 ? 0 : (int)(((long long)((l * g.shard_count + g.shard_index) / g.tiles_x) * n_chunks) / g.tiles_y); };
+    // chunks = bands of tile rows (only used unsharded), see bandFirstRow
+    auto chunkOf = [&](int l) { return n_chunks <= 1 ? 0 : bandOfRow((l * g.shard_count + g.shard_index) / g.tiles_x, n_chunks, g.tiles_y); };
     chunk_first.assign((size_t)n_chunks + 1, 0);
     for (int l = 0; l < g.n_local_tiles; ++l) chunk_first[(size_t)chunkOf(l) + 1]++;
     for (int k = 0; k < n_chunks; ++k) chunk_first[(size_t)k + 1] += chunk_first[(size_t)k];
@@ -825,7 +842,7 @@ int ftb_render(ftb_scene* scene, const ftb_camera* camera, const ftb_render_para
         const size_t rowBytes = outBytes(&p) / (size_t)p.height;
         const void* buf0 = pd->tiles.p;
         ChunkDone bandDone = [&](int c) -> int {
-            const int r0 = (c * full.tiles_y + kBands - 1) / kBands, r1 = ((c + 1) * full.tiles_y + kBands - 1) / kBands;
+            const int r0 = bandFirstRow(c, kBands, full.tiles_y), r1 = bandFirstRow(c + 1, kBands, full.tiles_y);
             const int y0 = std::min(p.height, r0 * FTB_TILE_H), y1 = std::min(p.height, r1 * FTB_TILE_H);
             if (y1 <= y0) return FTB_OK;
             int rc2 = launchAssemble(&p, full, &buf0, pd->out.p, pd->stream, y0, y1);

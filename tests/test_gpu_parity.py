@@ -254,6 +254,8 @@ def test_in_process_multi_gpu_render_matches_single_gpu():
     jit = frontend.jitter_pattern(2, spp)
     with api.Scene(sc) as scene:
         one = scene.render(W, H, spp, jit, out_format=abi.OUT_RGB_F32)["rgb"]
-        two = scene.render(W, H, spp, jit, out_format=abi.OUT_RGB_F32, n_gpus=2, stats=True)
+        two = scene.render(W, H, spp, jit, out_format=abi.OUT_RGB_F32, n_gpus=2)
+        counted = scene.render(W, H, spp, jit, out_format=abi.OUT_RGB_F32, n_gpus=2, stats=True)  # counting kernel = the generic variant
     assert (two["rgb"] == one).all()
-    assert two["stats"].primary_rays == W * H * spp
+    assert counted["stats"].primary_rays == W * H * spp
+    assert np.abs(counted["rgb"] - one).max() < 1e-3
