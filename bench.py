@@ -245,9 +245,18 @@ def main():
         pk = api.make_params(W, H, spp, jit, shard_index=k, shard_count=world, out_format=abi.OUT_RGB_F32)
         sizes.append(api.tile_buffer_bytes(pk))
     max_bytes = max(sizes)
+    arena = None
     if world > 1:
         tiles = torch.empty(max_bytes, dtype=torch.uint8, device=dev)  # equal-sized for gather
         gather_list = [torch.empty(max_bytes, dtype=torch.uint8, device=dev) for _ in range(world)] if rank == 0 else None
+        if not os.environ.get("FTB_NO_P2P"):
+            try:  # the render kernel writes its tiles straight into rank 0's memory over NVLink (functracer_b200/dist.py)
+                arena = fdist.PeerArena(max_bytes)
+            except Exception as e:  # no IPC / peer access: NCCL gather
+                arena = None
+                if rank == 0:
+                    print("peer arena unavailable (%s): falling back to the NCCL gather" % e, file=sys.stderr)
+    sync_flag = torch.zeros(1, dtype=torch.int32, device=dev)
     frame = torch.empty((H, W, 3), dtype=torch.float32, device=dev) if rank == 0 else None
     # L2 flush between timed iterations: 256 MB > the 126 MB L2
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
@@ -255,10 +264,14 @@ def main():
     def device_step(ev=None):
         if ev:
             ev[0].record()
-        scene.render_tiles_device(p_f32, tiles.data_ptr(), stream=stream)
+        scene.render_tiles_device(p_f32, arena.ptr(rank) if arena else tiles.data_ptr(), stream=stream)
         if ev:
             ev[1].record()
-        if world > 1:
+        if world > 1 and arena:
+            dist.all_reduce(sync_flag)  # the only collective: every rank's stores have landed before rank 0 assembles
+            if rank == 0:
+                api.assemble_device(p_f32, [arena.ptr(k) for k in range(world)], frame.data_ptr(), stream=stream)
+        elif world > 1:
             fdist.gather_tiles(tiles, max_bytes, gather_list)
             if rank == 0:
                 api.assemble_device(p_f32, [g.data_ptr() for g in gather_list], frame.data_ptr(), stream=stream)
@@ -307,10 +320,14 @@ def main():
         if world == 1:
             scene.render_params(p_host, out=out_np)  # H2D (jitter, frame constants) + kernels + D2H, synchronous
         else:
-            scene.render_tiles_device(p_f32, tiles.data_ptr(), stream=stream)
-            fdist.gather_tiles(tiles, max_bytes, gather_list)
+            scene.render_tiles_device(p_f32, arena.ptr(rank) if arena else tiles.data_ptr(), stream=stream)
+            if arena:
+                dist.all_reduce(sync_flag)
+            else:
+                fdist.gather_tiles(tiles, max_bytes, gather_list)
             if rank == 0:
-                api.assemble_device(p_f64out, [g.data_ptr() for g in gather_list], frame64.data_ptr(), stream=stream)
+                srcs = [arena.ptr(k) for k in range(world)] if arena else [g.data_ptr() for g in gather_list]
+                api.assemble_device(p_f64out, srcs, frame64.data_ptr(), stream=stream)
                 out_host.copy_(frame64, non_blocking=True)
             torch.cuda.synchronize()
 
@@ -329,6 +346,19 @@ def main():
     e2e_value = rays_per_frame * args.steps / e2e_s / 1e6
     clocks = sampler.stop() if sampler else None  # sampled over both timed regions
 
+    frame_check = None
+    if world > 1:  # outside every timed region: the sharded, peer-written frame equals rank 0's own unsharded render, bit for bit
+        device_step()
+        barrier()
+        if rank == 0:
+            p_one = api.make_params(W, H, spp, jit, seed=RNG_SEED, out_format=abi.OUT_RGB_F32)
+            t1 = torch.empty(api.tile_buffer_bytes(p_one), dtype=torch.uint8, device=dev)
+            f1 = torch.empty_like(frame)
+            scene.render_tiles_device(p_one, t1.data_ptr(), stream=stream)
+            api.assemble_device(p_one, [t1.data_ptr()], f1.data_ptr(), stream=stream)
+            torch.cuda.synchronize()
+            frame_check = "bit-exact vs the 1-GPU render" if bool((f1 == frame).all()) else "MISMATCH vs the 1-GPU render"
+        barrier()
     if rank == 0:
         peak, peak_how = _fp32_peak_tflops()
         kern_avg_ms = kern_total_ms / args.steps
@@ -341,10 +371,10 @@ def main():
             "config": {"workload": args.workload, "scene": cfg["build"].__name__, "width": W, "height": H, "spp": spp,
                        "recursion_limit": 8, "rays_per_frame": {"primary": n_primary, "shadow": n_shadow, "reflection": n_refl},
                        "tile": "16x16 round-robin over ranks", "l2": "flushed between timed iterations (256 MB write)",
-                       "parallelism": "tiles%d" % world},
+                       "parallelism": "tiles%d" % world, "gather": ("p2p-stores" if arena else "nccl-gather") if world > 1 else "none"},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": 1e3 * e2e_s / args.steps,
                     "h2d_bytes_per_step": int(16 * spp + 512), "d2h_bytes_per_step": int(W * H * 24),
-                    "call": "ftb_render (host RGB f64 frame)" if world == 1 else "ftb_render_tiles_device + NCCL gather + ftb_assemble_device + D2H",
+                    "call": "ftb_render (host RGB f64 frame)" if world == 1 else ("ftb_render_tiles_device (tiles stored into rank 0's memory over NVLink) + barrier + ftb_assemble_device + D2H" if arena else "ftb_render_tiles_device + NCCL gather + ftb_assemble_device + D2H"),
                     "scene_create_ms": create_ms},
             "gpu_launches": int(args.steps * (2 if world == 1 else (2 if rank == 0 else 1))),
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
@@ -354,6 +384,8 @@ def main():
                                      % (W * H * 12 // world, pk_how, pk.get("hbm_gbs", 0.0))},
             "clocks": clocks,
         }
+        if frame_check:
+            line["frame_check"] = frame_check
         if not args.no_cpu_baseline:
             windows = _sample_windows(W, H, 8, 8)
             rays, secs, cores = cpu_sample(parsed, jit, windows)
@@ -368,6 +400,9 @@ def main():
     scene.close()
     if world > 1:
         dist.barrier()
+        torch.cuda.synchronize()
+        if arena:
+            arena.close()
         dist.destroy_process_group()
 
 
