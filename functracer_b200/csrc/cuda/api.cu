@@ -883,18 +883,31 @@ int ftb_render(ftb_scene* scene, const ftb_camera* camera, const ftb_render_para
             if (dbg->sub_id) { CK(pd->dbg_sub.reserve((size_t)full.n_samples * 4)); CK(cudaMemsetAsync(pd->dbg_sub.p, 0, (size_t)full.n_samples * 4, pd->stream)); ddbg.sub_id = static_cast<int32_t*>(pd->dbg_sub.p); }
             if (dbg->t) { CK(pd->dbg_t.reserve((size_t)full.n_samples * 8)); CK(cudaMemsetAsync(pd->dbg_t.p, 0, (size_t)full.n_samples * 8, pd->stream)); ddbg.t = static_cast<double*>(pd->dbg_t.p); }
         }
-        if ((rc = launchFrameAny(scene, pd, camera, &ps, g, pd->tiles.p, ddbg.prim_id ? &ddbg : nullptr, stats, pd->stream, stats != nullptr)) != FTB_OK) return rc;
-        bufs[k] = pd->tiles.p;
-        if (k > 0) {  // gather over NVLink: peer copy into a staging buffer on the primary device
+        // Shards of the other devices: the render kernel's fold stores finished pixels straight into a buffer on the
+        // primary device over NVLink (peer access), so there is no gather step; without peer access the shard is
+        // rendered locally and copied with cudaMemcpyPeerAsync.
+        void* target = pd->tiles.p;
+        bool direct = false;
+        if (k > 0) {
             PerDevice* p0 = pds[0];
             if ((int)p0->peer_tiles.size() < n_gpus) p0->peer_tiles.resize(n_gpus);
             CK(cudaSetDevice(primary));
             CK(p0->peer_tiles[k].reserve(tileBytes));
             CK(cudaSetDevice(dev));
-            {  // direct NVLink path; without peer access the copy would be staged through the host
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, dev, primary) == cudaSuccess && can) {
                 cudaError_t pe = cudaDeviceEnablePeerAccess(primary, 0);
-                if (pe != cudaSuccess) (void)cudaGetLastError();  // already enabled / unsupported: the copy still works
+                if (pe == cudaSuccess || pe == cudaErrorPeerAccessAlreadyEnabled) direct = true;
+                (void)cudaGetLastError();
             }
+            static const bool noP2P = std::getenv("FTB_NO_P2P") != nullptr;  // A/B switch
+            if (noP2P) direct = false;
+            if (direct) target = p0->peer_tiles[k].p;
+        }
+        if ((rc = launchFrameAny(scene, pd, camera, &ps, g, target, ddbg.prim_id ? &ddbg : nullptr, stats, pd->stream, stats != nullptr)) != FTB_OK) return rc;
+        bufs[k] = target;
+        if (k > 0 && !direct) {
+            PerDevice* p0 = pds[0];
             CK(cudaMemcpyPeerAsync(p0->peer_tiles[k].p, primary, pd->tiles.p, dev, tileBytes, pd->stream));
             bufs[k] = p0->peer_tiles[k].p;
             if (stats) stats->kernel_launches += 1;
