@@ -375,7 +375,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": 1e3 * e2e_s / args.steps,
                     "h2d_bytes_per_step": int(16 * spp + 512), "d2h_bytes_per_step": int(W * H * 24),
                     "call": "ftb_render (host RGB f64 frame)" if world == 1 else ("ftb_render_tiles_device (tiles stored into rank 0's memory over NVLink) + barrier + ftb_assemble_device + D2H" if arena else "ftb_render_tiles_device + NCCL gather + ftb_assemble_device + D2H"),
-                    "scene_create_ms": create_ms},
+                    "scene_create_ms_first_call_incl_cuda_init": create_ms},
             "gpu_launches": int(args.steps * (2 if world == 1 else (2 if rank == 0 else 1))),
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "traffic": _traffic_per_launch(), "kernel": "ftb::render_kernel<float,false>", "kernel_ms": kern_avg_ms,

@@ -438,7 +438,7 @@ void fillStats(const Control& h, const ftb_scene& sc, ftb_stats* s)
     static const double F[9] = {28, 8, 8, 8, 26, 32, 20, 45, 0};
     double f = 0;
     for (int k = 0; k < 9; ++k) f += F[k] * (double)c[ST_LEAF0 + k];
-    f += 45.0 * (double)c[ST_TRI_TESTS_IN_MESH] + 33.0 * (double)c[ST_XFORM] + 12.0 * (double)c[ST_BSP_NODES] + 28.0 * (double)c[ST_BOUND_TESTS];
+    f += 45.0 * (double)c[ST_TRI_TESTS_IN_MESH] + 33.0 * (double)c[ST_XFORM] + 12.0 * (double)c[ST_BSP_NODES] + 17.0 * (double)c[ST_BOUND_TESTS];  // bound test: 3 sub + 2 dot (5 each) + 2 FMA
     f += (double)c[ST_SHADED] * (60.0 + 110.0 * (double)sc.lights.size()) + 18.0 * (double)c[ST_REFLECTION];
     s->flops += f;
 }
