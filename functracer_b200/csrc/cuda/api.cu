@@ -243,12 +243,25 @@ int uploadScene(const ftb_scene& sc, SceneStorage<R>& st)
     int rc;
 #define UP(vec, field) if ((rc = upload(st.allocs, vec, field)) != FTB_OK) return rc;
     {
-        std::vector<R4> w2m; std::vector<int4> meta;
+        std::vector<R4> w2m, p0; std::vector<int4> meta;
         for (const Leaf& lf : L.leaves) {
             for (int r = 0; r < 3; ++r) w2m.push_back(Mk4<R>::make(lf.w2m[4 * r], lf.w2m[4 * r + 1], lf.w2m[4 * r + 2], lf.w2m[4 * r + 3]));
-            meta.push_back(make_int4(lf.kind | (lf.identity << 8), lf.surface, lf.prim, lf.payload));
+            {  // world point of the model origin: solve A p0 + b = 0 (Cramer; singular matrices keep p0 = 0)
+                const double* m = lf.w2m;
+                const double c00 = m[5] * m[10] - m[6] * m[9], c01 = m[6] * m[8] - m[4] * m[10], c02 = m[4] * m[9] - m[5] * m[8];
+                const double det = m[0] * c00 + m[1] * c01 + m[2] * c02;
+                double q[3] = {0, 0, 0};
+                if (std::fabs(det) > 0 && std::isfinite(det)) {
+                    const double id = 1.0 / det, bx = -m[3], by = -m[7], bz = -m[11];
+                    q[0] = (bx * c00 + by * (m[2] * m[9] - m[1] * m[10]) + bz * (m[1] * m[6] - m[2] * m[5])) * id;
+                    q[1] = (bx * c01 + by * (m[0] * m[10] - m[2] * m[8]) + bz * (m[2] * m[4] - m[0] * m[6])) * id;
+                    q[2] = (bx * c02 + by * (m[1] * m[8] - m[0] * m[9]) + bz * (m[0] * m[5] - m[1] * m[4])) * id;
+                }
+                p0.push_back(Mk4<R>::make(q[0], q[1], q[2], 0));
+            }
+            meta.push_back(make_int4(lf.kind | (lf.identity << 8) | (lf.top_level << 9), lf.surface, lf.prim, lf.payload));
         }
-        UP(w2m, v.leaf_w2m) UP(meta, v.leaf_meta)
+        UP(w2m, v.leaf_w2m) UP(meta, v.leaf_meta) UP(p0, v.leaf_p0)
         v.n_leaves = (int)L.leaves.size();
     }
     {

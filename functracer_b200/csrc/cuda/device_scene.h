@@ -38,7 +38,8 @@ enum Feature : unsigned {
     FT_ROUGH = 0x20,  // Oren-Nayar diffuse
     FT_RNG = 0x40,    // soft directional lights, depth of field
     FT_CSGN = 0x80,   // any other CSG item (general post-order program, inlined)
-    FT_ALL = 0xff
+    FT_PLANAR = 0x100,  // a top-level plane / square / circle leaf exists (FP32 self-intersection guard, render.cuh)
+    FT_ALL = 0x1ff
 };
 
 enum StatSlot : int {
@@ -60,6 +61,7 @@ struct DevScene {
     typedef typename V4<R>::type R4;
     // leaves
     const R4* leaf_w2m;     // 3 rows per leaf
+    const R4* leaf_p0;      // per leaf: the world point that maps to the model origin (a point of the plane for planar leaves)
     const int4* leaf_meta;  // x = kind | identity << 8, y = surface, z = prim, w = payload
     int n_leaves;
     // top-level items in enumeration order

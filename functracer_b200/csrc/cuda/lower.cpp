@@ -386,7 +386,10 @@ struct Lowerer {
         case FTB_NODE_PRIMITIVE: {
             std::vector<int> lv;
             if (!primitiveLeaves(n, cx, lv)) return false;
-            for (int l : lv) pushItem(ITEM_LEAF, l, 0, L.surfaces[L.leaves[l].surface].apply_lighting != 0, leafBound[l], false);
+            for (int l : lv) {
+                L.leaves[l].top_level = 1;
+                pushItem(ITEM_LEAF, l, 0, L.surfaces[L.leaves[l].surface].apply_lighting != 0, leafBound[l], false);
+            }
             return true;
         }
         case FTB_NODE_TRANSFORM:
@@ -620,6 +623,8 @@ int lower_scene(const ftb_scene_desc& d, Lowered& out, std::string& err)
     if (out.has_texture) f |= 0x10;
     if (out.has_rough) f |= 0x20;
     if (out.has_soft_light) f |= 0x40;
+    for (const Leaf& lf : out.leaves)
+        if (lf.top_level && (lf.kind == LEAF_PLANE || lf.kind == LEAF_SQUARE || lf.kind == LEAF_CIRCLE)) f |= 0x100;
     out.features = f;
     if (out.has_mesh) buildMeshIndex(d, out);
     return FTB_OK;

@@ -55,7 +55,8 @@ struct Leaf {
     int32_t prim;     // depth-first PRIMITIVE-instance index (the debug plane's prim_id)
     int32_t payload;  // mesh index | triangle index | solidCylinder part (reported as sub_id)
     int32_t identity; // 1 = w2m is the identity (no transform on the path)
-    int32_t reserved[3];
+    int32_t top_level; // 1 = the leaf is an item of its own (not an operand of a CSG node)
+    int32_t reserved[2];
     double w2m[12];   // composed world->model, row-major 3x4
 };
 
@@ -129,7 +130,7 @@ struct Lowered {
     bool has_csg = false, has_mesh = false, has_texture = false, has_image = false;
     bool has_soft_light = false, has_rough = false, has_reflection = false;
     // Kernel features this scene needs, as device_scene.h `Feature` bits (cube 1, round 2, mesh 4, csg 8,
-    // texture 16, Oren-Nayar 32, rng 64, general CSG 128); camera depth of field adds rng at render time.
+    // texture 16, Oren-Nayar 32, rng 64, general CSG 128, top-level planar leaf 256); camera depth of field adds rng at render time.
     unsigned features = 0;
 };
 

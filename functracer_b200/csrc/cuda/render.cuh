@@ -683,7 +683,7 @@ struct HitInfo {
 //   any = false: Scene.intersectScene = geometry >> closest (Scene.fs:112-118); limit = +inf.
 //   any = true : Scene.lightIsBocked (Scene.fs:119-121); limit = maxDistance; leaf >= 0 means blocked.
 template <typename R, unsigned FEAT, bool STATS>
-FTB_DEV HitInfo<R> traceScene(const DevScene<R>& S, const Ray<R>& wr, R limit, bool any, bool& overflow, Counters<STATS>& cn)
+FTB_DEV HitInfo<R> traceScene(const DevScene<R>& S, const Ray<R>& wr, R limit, bool any, int skipLeaf, bool& overflow, Counters<STATS>& cn)
 {
     typedef typename V4<R>::type R4;
     RaySink<R> best;
@@ -717,8 +717,10 @@ FTB_DEV HitInfo<R> traceScene(const DevScene<R>& S, const Ray<R>& wr, R limit, b
             cand &= cand - 1;
             const int4 item = __ldg(S.items + it);
             if (item.x == ITEM_LEAF) {
-                best.cur = item.y;
-                intersectLeaf<R, FEAT, STATS>(S, item.y, wr, best, cn);
+                if (item.y != skipLeaf) {  // skipLeaf: the planar leaf this ray leaves and cannot meet again (FP32 build, see the kernel)
+                    best.cur = item.y;
+                    intersectLeaf<R, FEAT, STATS>(S, item.y, wr, best, cn);
+                }
             } else if constexpr ((FEAT & (FT_CSG | FT_CSGN)) != 0) {
                 bool done = false;
                 if constexpr ((FEAT & FT_CSG) != 0) {
@@ -824,6 +826,7 @@ struct Fragment {
     Vec<R> colour;
     R roughness, reflectance, shineyness;
     bool applyLighting;
+    int planarLeaf;  // FP32 build: the hit is on a top-level planar leaf (index), else -1
 };
 
 template <typename R, unsigned FEAT>
@@ -863,6 +866,7 @@ FTB_DEV Fragment<R> finalise(const DevScene<R>& S, const Ray<R>& wr, const HitIn
         }
     }
     Fragment<R> f;
+    f.planarLeaf = -1;
     const int4 si = __ldg(S.surf_i + meta.y);
     // n <- normalise(normalToWorld * n), normalToWorld = transpose(worldToModel) (Transform.fs:83,86)
     Vec<R> nw = nm;
@@ -874,6 +878,19 @@ FTB_DEV Fragment<R> finalise(const DevScene<R>& S, const Ray<R>& wr, const HitIn
     f.n = nw;
     // p = modelToWorld * p_model == o + t d in exact arithmetic (t is invariant); the ray itself is used
     f.p = mk<R>(wr.o.x + h.t * wr.d.x, wr.o.y + h.t * wr.d.y, wr.o.z + h.t * wr.d.z);
+    if constexpr (sizeof(R) == 4 && (FEAT & FT_PLANAR) != 0) {
+        // FP32 only: a hit on a planar leaf far from the origin (the horizon of a ground plane, |p| ~ 1e3) is off the plane
+        // by |p| * 6e-8, which is more than the reference's fixed 1e-4 d / 1e-4 n offsets can absorb: reflection rays
+        // re-hit the plane from below (seen as a 1 / (1 - reflectance) brightening).  Put p back on the plane: with
+        // p0 a world point of the plane, p -= ((p - p0).n) n - exact for axis-aligned planes, harmless for the others.
+        if (kind == LEAF_PLANE || kind == LEAF_SQUARE || kind == LEAF_CIRCLE) {
+            const R4 q = ldg4<R>(S.leaf_p0 + h.leaf);
+            const Vec<R> n1 = h.flip ? -nw : nw;
+            const R off = (f.p.x - q.x) * n1.x + (f.p.y - q.y) * n1.y + (f.p.z - q.z) * n1.z;
+            f.p = mk<R>(f.p.x - off * n1.x, f.p.y - off * n1.y, f.p.z - off * n1.z);
+            if ((meta.x >> 9) & 1) f.planarLeaf = h.leaf;
+        }
+    }
     const R4 sa = ldg4<R>(S.surf_a + meta.y), sb = ldg4<R>(S.surf_b + meta.y);
     Vec<R> col = mk<R>(sa.x, sa.y, sa.z);
     if constexpr ((FEAT & FT_TEX) != 0) {
@@ -1159,7 +1176,15 @@ __global__ void __launch_bounds__(kBlockThreads, FTB_MIN_BLOCKS) render_kernel(c
             tr.o = ray.o + R(0.0001) * ray.d;
             pathD = ray.d;
         } else cn.add(ST_SHADOW);
-        const HitInfo<R> h = traceScene<R, FEAT, STATS>(S, tr, phase == PH_NEAREST ? inf_<R>() : tmax, phase == PH_SHADOW, overflow, cn);
+        // FP32 build: a ray that starts on a top-level plane / square / circle and heads away from it has no crossing with
+        // that leaf at t >= 0 (the reference's 1e-4 offsets put the only crossing at t < 0).  Far from the origin FP32 cannot
+        // represent those offsets (at the horizon of a ground plane 1e-4 * d.y ~ 1e-8 next to |y| ~ 2), the crossing lands
+        // on t = 0 or beyond and the plane reflects / shadows itself.  Such rays skip that one leaf; nothing else changes.
+        int skipLeaf = -1;
+        if constexpr (sizeof(R) == 4 && (FEAT & FT_PLANAR) != 0) {  // `f` is still the fragment this bounce / shadow ray starts from
+            if (f.planarLeaf >= 0 && (phase == PH_NEAREST ? depth > 0 : dot(ray.d, f.n) >= R(0))) skipLeaf = f.planarLeaf;
+        }
+        const HitInfo<R> h = traceScene<R, FEAT, STATS>(S, tr, phase == PH_NEAREST ? inf_<R>() : tmax, phase == PH_SHADOW, skipLeaf, overflow, cn);
 
         // ---- consume the result -----------------------------------------------------------------------------------------
         bool got = false;       // an intensity for light `li` is ready
