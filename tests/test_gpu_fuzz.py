@@ -78,9 +78,17 @@ def _geometry(rng, depth, in_csg=False):
 def _scene(seed):
     rng = np.random.default_rng(seed)
     cam = "camera pos (%s,%s,%s) lookat (0,0,0) up (0,1,0) fov 55 ratio 1" % (_num(rng.uniform(-1, 1)), _num(rng.uniform(0.5, 2.5)), _num(rng.uniform(-6.5, -5)))
+    if rng.random() < 0.2:  # depth of field (Image.fs:91-94)
+        cam += " focus (%s,%s)" % (_num(rng.uniform(4, 8)), _num(rng.uniform(0.5, 3)))
+    samples = "samples corner" if rng.random() < 0.1 else "samples %d" % int(rng.integers(1, 4))
     objs = []
     for _ in range(int(rng.integers(1, 5))):
         objs.append("(translate %s %s)" % (_t(rng, -1.8, 1.8), _geometry(rng, 4)))
+    if rng.random() < 0.2:  # a mesh (never a CSG operand: Triangle.fs:62 emits no t < 0 crossings)
+        objs.append('(%s (translate %s (scale %s (translate (0.017,-0.11,0) %s "bunny_tiny.ply"))))' % (
+            _material(rng), _t(rng, -1.5, 1.5), _num(rng.uniform(6, 12)), rng.choice(["mesh", "bspMesh 0", "bspMesh 3"])))
+    if rng.random() < 0.15:  # image texture on a sphere
+        objs.append('(texture image "moon.ppm" (translate %s sphere))' % _t(rng, -1.5, 1.5))
     if rng.random() < 0.7:
         objs.append("(%s (translate (0,-2.2,0) plane))" % _material(rng))
     lights = []
@@ -93,15 +101,15 @@ def _scene(seed):
         else:
             lights.append("softdirectional dir (%s,%s,%s) samples %d scatter %s colour %s" % (_num(rng.uniform(-1, 1)), _num(rng.uniform(-1.5, -0.3)), _num(rng.uniform(-1, 1)),
                                                                                            int(rng.integers(1, 4)), _num(rng.uniform(2, 30)), _colour(rng)))
-    return cam + "\nsamples 2\nres 56 40\n\n" + "\n\n".join(objs) + "\n\n" + "\n".join(lights) + "\n"
+    return cam + "\n" + samples + "\nres 56 40\n\n" + "\n\n".join(objs) + "\n\n" + "\n".join(lights) + "\n"
 
 
-@pytest.mark.parametrize("seed", range(80))
+@pytest.mark.parametrize("seed", range(160))
 def test_random_scene(seed):
     text = _scene(1000 + seed)
     sc = parse(text)
     jit = frontend.jitter_pattern(seed + 1, sc.spp)
-    ref = orc.render(sc, orc.make_params(sc.width, sc.height, sc.spp, jit, seed=77))
+    ref = orc.render(sc, orc.make_params(sc.width, sc.height, sc.spp, jit, seed=77, sampling=sc.sampling))
     try:
         scene = api.Scene(sc)
     except api.FtbError as e:
@@ -109,8 +117,8 @@ def test_random_scene(seed):
         pytest.skip("unsupported by the device path: %s" % e)
     with scene:
         try:
-            g64 = scene.render(sc.width, sc.height, sc.spp, jit, seed=77, precision=abi.PRECISION_FP64_VERIFY, debug=True)
-            g32 = scene.render(sc.width, sc.height, sc.spp, jit, seed=77, precision=abi.PRECISION_FP32, debug=True)
+            g64 = scene.render(sc.width, sc.height, sc.spp, jit, seed=77, precision=abi.PRECISION_FP64_VERIFY, debug=True, sampling=sc.sampling)
+            g32 = scene.render(sc.width, sc.height, sc.spp, jit, seed=77, precision=abi.PRECISION_FP32, debug=True, sampling=sc.sampling)
         except api.FtbError as e:
             assert e.status == abi.ERR_HIT_OVERFLOW, text
             pytest.skip("hit-stack overflow reported: %s" % e)

@@ -12,11 +12,11 @@ for seed in [int(x) for x in sys.argv[1:]]:
     print("=" * 30, seed); print(text)
     sc = parse(text)
     jit = frontend.jitter_pattern(seed + 1, sc.spp)
-    ref = orc.render(sc, orc.make_params(sc.width, sc.height, sc.spp, jit, seed=77))
+    ref = orc.render(sc, orc.make_params(sc.width, sc.height, sc.spp, jit, seed=77, sampling=sc.sampling))
     with api.Scene(sc) as scene:
         for prec in (abi.PRECISION_FP64_VERIFY, abi.PRECISION_FP32):
             try:
-                g = scene.render(sc.width, sc.height, sc.spp, jit, seed=77, precision=prec, debug=True)
+                g = scene.render(sc.width, sc.height, sc.spp, jit, seed=77, precision=prec, debug=True, sampling=sc.sampling)
             except api.FtbError as e:
                 print("prec", prec, "ERROR", e); continue
             mm = np.nonzero(g["prim"] != ref["prim"])[0]
