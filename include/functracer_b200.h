@@ -241,12 +241,13 @@ typedef struct ftb_stats {
     uint64_t shadow_rays;
     uint64_t reflection_rays; /* unique reflection rays */
     uint64_t shaded_hits;
-    uint64_t leaf_tests[10];  /* by ftb_prim_kind; cube / solidCylinder counted once per primitive */
+    uint64_t leaf_tests[10];  /* by ftb_prim_kind; a cube counts once, the three parts of a solidCylinder count as
+                                 2 circles + 1 cylinder, mesh triangles tested count under FTB_PRIM_TRIANGLE */
     uint64_t transformed_leaf_tests;
-    uint64_t bsp_nodes_visited;
+    uint64_t bsp_nodes_visited; /* nodes of the device's mesh index (a BVH over the BSP's triangles) visited */
     uint64_t bound_tests;     /* object-level bound tests (no counterpart in the reference) */
     uint64_t csg_ops;
-    double flops;             /* algorithmic flops by the SURVEY.md 8(d) table */
+    double flops;             /* algorithmic flops by the SURVEY.md 8(d) table (+ 17 per bound test) */
     double kernel_ms;         /* device time of the render kernel(s) */
     double total_ms;          /* wall time of the call */
     int32_t kernel_launches;
