@@ -13,13 +13,8 @@ type FtbNode =
     val mutable reserved: int
     new (k, a, b) = { kind = k; a = a; b = b; reserved = 0 }
 
-// 12 + 12 doubles, row-major 3x4: m2w = matrix t, w2m = matrix (inverse t)   (Transform.fs:55-71, 81-82)
-[<Struct; StructLayout(LayoutKind.Sequential)>]
-type FtbTransform =
-    [<MarshalAs(UnmanagedType.ByValArray, SizeConst = 12)>]
-    val mutable m2w: float[]
-    [<MarshalAs(UnmanagedType.ByValArray, SizeConst = 12)>]
-    val mutable w2m: float[]
+// ftb_transform = 12 + 12 doubles, row-major 3x4: m2w = matrix t, w2m = matrix (inverse t) (Transform.fs:55-71, 81-82).
+// It is passed as a plain float[] of 24 doubles per transform (SceneFlatten), so no struct is declared for it.
 
 [<Struct; StructLayout(LayoutKind.Sequential)>]
 type FtbMaterial =

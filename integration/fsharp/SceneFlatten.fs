@@ -18,7 +18,7 @@ let private primKind = function
 type Tables () =
     member val nodes = List<FtbNode>()
     member val children = List<int>()
-    member val transforms = List<FtbTransform>()
+    member val transforms = List<float>()   // 24 doubles per ftb_transform (m2w rows, then w2m rows): a blittable float[] pins, a struct holding arrays would not
     member val materials = List<FtbMaterial>()
     member val textures = List<FtbTexture>()
     member val images = List<byte[] * int * int>()
@@ -82,9 +82,9 @@ let rec private addNode (t: Tables) (g: SceneGraph) : int =
         let c = addNode t child
         match f with
         | Transform tr ->
-            t.transforms.Add (FtbTransform (m2w = rows34 (Transform.matrix tr |> Transform.toArray),
-                                            w2m = rows34 (Transform.matrix (Transform.inverse tr) |> Transform.toArray)))
-            emit (FtbNode (1, t.transforms.Count - 1, c))
+            t.transforms.AddRange (rows34 (Transform.matrix tr |> Transform.toArray))
+            t.transforms.AddRange (rows34 (Transform.matrix (Transform.inverse tr) |> Transform.toArray))
+            emit (FtbNode (1, t.transforms.Count / 24 - 1, c))
         | Material m ->
             let (Colour (r, g, b)) = m.colour
             t.materials.Add (FtbMaterial (r = r, g = g, b = b, roughness = m.roughness, reflectance = m.reflectance,
@@ -125,7 +125,7 @@ type Flattened (scene: Scene, camera: Image.Camera) =
         FtbSceneDesc (root = root,
                       nNodes = t.nodes.Count, nodes = pin (t.nodes.ToArray ()),
                       nChildren = t.children.Count, children = pin (t.children.ToArray ()),
-                      nTransforms = t.transforms.Count, transforms = pin (t.transforms.ToArray ()),
+                      nTransforms = t.transforms.Count / 24, transforms = pin (t.transforms.ToArray ()),
                       nMaterials = t.materials.Count, materials = pin (t.materials.ToArray ()),
                       nTextures = t.textures.Count, textures = pin (t.textures.ToArray ()),
                       nImages = imageRows.Length, images = pin imageRows,
