@@ -14,7 +14,10 @@ constexpr int kBspStack = 64;  // per-ray BSP traversal stack
 constexpr int kBlockThreads = 128;
 // most samples of one unit of the blend ring (render.cuh): a launch covers at most this many samples per pixel,
 // frames with more are rendered in several passes that continue the same left fold
-template <typename R> struct UnitCap { static constexpr int value = sizeof(R) == 4 ? 128 : 64; };
+#ifndef FTB_UNIT_CAP
+#define FTB_UNIT_CAP 128
+#endif
+template <typename R> struct UnitCap { static constexpr int value = sizeof(R) == 4 ? FTB_UNIT_CAP : 64; };
 
 template <typename R>
 struct V4;

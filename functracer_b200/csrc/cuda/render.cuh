@@ -990,13 +990,16 @@ FTB_DEV Ray<R> primaryRay(const DevFrame<R>& F, int px, int py, int s, unsigned 
 #endif
 enum Phase : int { PH_IDLE = 0, PH_NEAREST = 1, PH_SHADOW = 2, PH_START = 3 };
 
-// Blend ring: every warp keeps kRingSlots units in flight; a unit is a run of pixels of one 8x4 block times the
+// Blend ring: every warp keeps up to kRingSlots units in flight; a unit is a run of pixels of one 8x4 block times the
 // samples of this pass (<= UnitCap<R> samples).  Lanes take SAMPLES, not pixels: the longest sequential chain a lane
 // can be stuck with is one sample's bounce chain, not spp of them, which is what bounds the kernel's tail and its
 // strong scaling.  Finished sample colours are parked in the unit's slot in shared memory; when the last sample of a
 // unit lands, the warp folds each pixel's samples IN SAMPLE ORDER (Array.average folds from Zero, Image.fs:112-116),
 // so the frame does not depend on which lane traced which sample, nor on timing.
-constexpr int kRingSlots = 4;
+#ifndef FTB_RING_SLOTS
+#define FTB_RING_SLOTS 2  // measured: 1 starves cheap-sample scenes (moon +70 %), 2 beats 3 and 4 by 1-3 % (fewer warp-uniform registers)
+#endif
+constexpr int kRingSlots = FTB_RING_SLOTS;
 
 // Folds a completed unit: every pixel's samples of this pass, in sample order, onto the running sum of the earlier
 // passes; the last pass divides by the frame's sample count (Array.average = fold (+) Zero, then DivideByInt;
