@@ -426,6 +426,7 @@ void fillCamera(DevFrame<R>& F, const ftb_camera& c, int resH, int resV)
     double pixelHeight = height / (double)(resH - 1);  // the reference's swapped axes (Image.fs:71-72)
     double pixelWidth = width / (double)(resV - 1);
     F.cam_o[0] = (R)o.x; F.cam_o[1] = (R)o.y; F.cam_o[2] = (R)o.z;
+    F.primary_slack = (R)(2e-4 * std::sqrt(o.x * o.x + o.y * o.y + o.z * o.z));
     F.cam_k[0] = (R)k.x; F.cam_k[1] = (R)k.y; F.cam_k[2] = (R)k.z;
     F.cam_i[0] = (R)i.x; F.cam_i[1] = (R)i.y; F.cam_i[2] = (R)i.z;
     F.cam_j[0] = (R)j.x; F.cam_j[1] = (R)j.y; F.cam_j[2] = (R)j.z;
@@ -446,12 +447,13 @@ void fillStats(const Control& h, const ftb_scene& sc, ftb_stats* s)
     static const int slot[9] = {FTB_PRIM_SPHERE, FTB_PRIM_PLANE, FTB_PRIM_SQUARE, FTB_PRIM_CIRCLE, FTB_PRIM_CYLINDER, FTB_PRIM_CONE, FTB_PRIM_CUBE, FTB_PRIM_TRIANGLE, FTB_PRIM_BSPMESH};
     for (int k = 0; k < 9; ++k) s->leaf_tests[slot[k]] += c[ST_LEAF0 + k];
     s->leaf_tests[FTB_PRIM_TRIANGLE] += c[ST_TRI_TESTS_IN_MESH];
-    s->transformed_leaf_tests += c[ST_XFORM]; s->bsp_nodes_visited += c[ST_BSP_NODES]; s->bound_tests += c[ST_BOUND_TESTS]; s->csg_ops += c[ST_CSG_OPS];
+    s->transformed_leaf_tests += c[ST_XFORM]; s->bsp_nodes_visited += c[ST_BSP_NODES]; s->bound_tests += c[ST_BOUND_TESTS] + c[ST_BOUND_FAST]; s->csg_ops += c[ST_CSG_OPS];
     // algorithmic flops, SURVEY.md 8(d) table (FMA = 2; compares / selects = 0)
     static const double F[9] = {28, 8, 8, 8, 26, 32, 20, 45, 0};
     double f = 0;
     for (int k = 0; k < 9; ++k) f += F[k] * (double)c[ST_LEAF0 + k];
-    f += 45.0 * (double)c[ST_TRI_TESTS_IN_MESH] + 33.0 * (double)c[ST_XFORM] + 12.0 * (double)c[ST_BSP_NODES] + 17.0 * (double)c[ST_BOUND_TESTS];  // bound test: 3 sub + 2 dot (5 each) + 2 FMA
+    f += 45.0 * (double)c[ST_TRI_TESTS_IN_MESH] + 33.0 * (double)c[ST_XFORM] + 12.0 * (double)c[ST_BSP_NODES] + 17.0 * (double)c[ST_BOUND_TESTS]   // bound test: 3 sub + 2 dot (5 each) + 2 FMA
+         + 5.0 * (double)c[ST_BOUND_FAST];  // common-origin form: one dot
     f += (double)c[ST_SHADED] * (60.0 + 110.0 * (double)sc.lights.size()) + 18.0 * (double)c[ST_REFLECTION];
     s->flops += f;
 }
@@ -562,6 +564,7 @@ int launchFrame(ftb_scene* sc, PerDevice* pd, const ftb_camera* cam, const ftb_r
     std::memset(&F, 0, sizeof(F));
     F.mode = 0;
     F.gw = g.gw; F.gh = g.gh; F.spp = g.spp; F.tiles_x = g.tiles_x;
+    F.tiles_x_magic = ((unsigned long long)g.n_tiles * (unsigned long long)g.tiles_x < (1ull << 32)) ? (unsigned)((1ull << 32) / (unsigned)g.tiles_x) + 1u : 0u;
     F.n_local_tiles = g.n_local_tiles; F.shard_index = g.shard_index; F.shard_count = g.shard_count;
     fillCamera<R>(F, *cam, p->width, p->height);
     if (!g.corner) {

@@ -56,6 +56,7 @@ enum StatSlot : int {
     ST_BOUND_TESTS,
     ST_CSG_OPS,
     ST_TRI_TESTS_IN_MESH,
+    ST_BOUND_FAST,  // bound tests answered from the common-origin table (one dot product + compare)
     ST_COUNT
 };
 
@@ -111,11 +112,13 @@ struct DevFrame {
     int bw_log, bh_log;   // the work queue hands out blocks of (1 << bw_log) x (1 << bh_log) pixels (bw <= 8)
     int n_blocks;         // blocks (mode 0) or groups of 32 rays (mode 1) in the queue
     int tiles_x;
+    unsigned tiles_x_magic;  // floor(2^32 / tiles_x) + 1: tile / tiles_x == __umulhi(tile, magic); 0 = frame too large for that, divide
     int n_local_tiles;  // tiles this shard renders
     int shard_index, shard_count;
     long long n_rays;  // mode 1
     R cam_o[3], cam_k[3], cam_i[3], cam_j[3];
     R pw, ph, tlx, tly;
+    R primary_slack;  // 2e-4 |cam_o|: see the common-origin bound table in render.cuh
     int has_focus;
     R focal, tan_half_aperture;
     const R* jitter;     // 2 * spp

@@ -619,14 +619,6 @@ struct PairSink {
 template <typename R, unsigned FEAT, bool STATS>
 FTB_DEV bool csgPair(const DevScene<R>& S, int leafA, int leafB, int op, const Ray<R>& wr, RaySink<R>& best, Counters<STATS>& cn)
 {
-    PairSink<R> a, b;
-    a.n = 0; a.t0 = a.t1 = R(0); a.s0 = a.s1 = 0;
-    b.n = 0; b.t0 = b.t1 = R(0); b.s0 = b.s1 = 0;
-    intersectLeaf<R, FEAT & ~FT_MESH, STATS>(S, leafA, wr, a, cn);
-    if (a.n > 2) return false;
-    intersectLeaf<R, FEAT & ~FT_MESH, STATS>(S, leafB, wr, b, cn);
-    if (b.n > 2) return false;
-    cn.add(ST_CSG_OPS);
     R mt[4];
     unsigned mid[4];
     int mn = 0;
@@ -642,6 +634,14 @@ FTB_DEV bool csgPair(const DevScene<R>& S, int leafA, int leafB, int op, const R
         for (int i = 0; i < 4; ++i) if (i == p) { mt[i] = t; mid[i] = id; }
         ++mn;
     };
+    PairSink<R> a, b;
+    a.n = 0; a.t0 = a.t1 = R(0); a.s0 = a.s1 = 0;
+    b.n = 0; b.t0 = b.t1 = R(0); b.s0 = b.s1 = 0;
+    intersectLeaf<R, FEAT & ~FT_MESH, STATS>(S, leafA, wr, a, cn);
+    if (a.n > 2) return false;
+    intersectLeaf<R, FEAT & ~FT_MESH, STATS>(S, leafB, wr, b, cn);
+    if (b.n > 2) return false;
+    cn.add(ST_CSG_OPS);
     if (a.n > 0) insert(a.t0, (unsigned)leafA | ((unsigned)(a.s0 & 7) << kIdSubShift));
     if (a.n > 1) insert(a.t1, (unsigned)leafA | ((unsigned)(a.s1 & 7) << kIdSubShift));
     if (b.n > 0) insert(b.t0, (unsigned)leafB | ((unsigned)(b.s0 & 7) << kIdSubShift) | kIdSideB);
@@ -682,8 +682,11 @@ struct HitInfo {
 // One ray against the whole scene.
 //   any = false: Scene.intersectScene = geometry >> closest (Scene.fs:112-118); limit = +inf.
 //   any = true : Scene.lightIsBocked (Scene.fs:119-121); limit = maxDistance; leaf >= 0 means blocked.
+//   tab != nullptr (warp-uniform): every lane of this call traces a ray whose bound tests can be answered from its row
+//   of the common-origin table (primary rays from the camera, shadow rays towards a point light; built in the kernel's
+//   prologue); tabSlack = how far the ray's actual line can pass from that common point, as a distance along the ray.
 template <typename R, unsigned FEAT, bool STATS>
-FTB_DEV HitInfo<R> traceScene(const DevScene<R>& S, const Ray<R>& wr, R limit, bool any, int skipLeaf, bool& overflow, Counters<STATS>& cn)
+FTB_DEV HitInfo<R> traceScene(const DevScene<R>& S, const Ray<R>& wr, R limit, bool any, int skipLeaf, const typename V4<R>::type* tab, R tabSlack, bool& overflow, Counters<STATS>& cn)
 {
     typedef typename V4<R>::type R4;
     RaySink<R> best;
@@ -697,18 +700,28 @@ FTB_DEV HitInfo<R> traceScene(const DevScene<R>& S, const Ray<R>& wr, R limit, b
         // of its stall samples waiting on these two loads).
         const int n = min(32, S.n_items - base);
         unsigned cand = 0;
+        if (tab) {  // rays from a common origin: |oc|, the miss and the behind test fold into one threshold per (origin, item)
 #pragma unroll 4
-        for (int j = 0; j < n; ++j) {
-            const R4 bound = ldg4<R>(S.item_bound + base + j);  // xyz = centre, w = inflated radius^2 (< 0: unbounded)
-            const Vec<R> oc = mk<R>(bound.x - wr.o.x, bound.y - wr.o.y, bound.z - wr.o.z);
-            const R b = dot(oc, du);                                 // distance along the ray to the point nearest the centre
-            const R oc2 = dot(oc, oc);
-            // |centre - line|^2 = oc2 - b^2; the 1e-6 oc2 slack covers the cancellation (and the radius is inflated)
-            const bool miss = oc2 - b * b > bound.w + R(1e-6) * oc2;  // the ray's line misses the bound: no crossing at all
-            const bool behind = b < R(0) && oc2 > bound.w;            // bound entirely behind the origin: every crossing has t < 0
-            const bool unbounded = bound.w < R(0);
-            cn.add(ST_BOUND_TESTS, unbounded ? 0u : 1u);
-            cand |= (unbounded || !(miss || behind)) ? (1u << j) : 0u;
+            for (int j = 0; j < n; ++j) {
+                const R4 e = tab[base + j];  // xyz = centre - origin (origin - centre for a light: the ray points AT it), w = threshold
+                const R b = e.x * du.x + (e.y * du.y + (e.z * du.z + tabSlack));
+                cn.add(ST_BOUND_FAST, e.w > -inf_<R>() ? 1u : 0u);
+                cand |= !(b < e.w) ? (1u << j) : 0u;  // NaN stays a candidate, like the general form
+            }
+        } else {
+#pragma unroll 4
+            for (int j = 0; j < n; ++j) {
+                const R4 bound = ldg4<R>(S.item_bound + base + j);  // xyz = centre, w = inflated radius^2 (< 0: unbounded)
+                const Vec<R> oc = mk<R>(bound.x - wr.o.x, bound.y - wr.o.y, bound.z - wr.o.z);
+                const R b = dot(oc, du);                                 // distance along the ray to the point nearest the centre
+                const R oc2 = dot(oc, oc);
+                // |centre - line|^2 = oc2 - b^2; the 1e-6 oc2 slack covers the cancellation (and the radius is inflated)
+                const bool miss = oc2 - b * b > bound.w + R(1e-6) * oc2;  // the ray's line misses the bound: no crossing at all
+                const bool behind = b < R(0) && oc2 > bound.w;            // bound entirely behind the origin: every crossing has t < 0
+                const bool unbounded = bound.w < R(0);
+                cn.add(ST_BOUND_TESTS, unbounded ? 0u : 1u);
+                cand |= (unbounded || !(miss || behind)) ? (1u << j) : 0u;
+            }
         }
         if (any) cand &= __ldg(S.item_casts + (base >> 5));  // items with nothing that has applyLighting cannot block (Scene.fs:121)
         // ---- phase B: this lane's candidates, in enumeration order (lanes walk their own lists) -----------------
@@ -1000,6 +1013,10 @@ enum Phase : int { PH_IDLE = 0, PH_NEAREST = 1, PH_SHADOW = 2, PH_START = 3 };
 #define FTB_RING_SLOTS 2  // measured: 1 starves cheap-sample scenes (moon +70 %), 2 beats 3 and 4 by 1-3 % (fewer warp-uniform registers)
 #endif
 constexpr int kRingSlots = FTB_RING_SLOTS;
+#ifndef FTB_FAST_BOUNDS
+#define FTB_FAST_BOUNDS 1
+#endif
+constexpr int kOriginCap = 256;  // rows x items of the common-origin bound table (4 KB of shared memory in FP32)
 
 // Folds a completed unit: every pixel's samples of this pass, in sample order, onto the running sum of the earlier
 // passes; the last pass divides by the frame's sample count (Array.average = fold (+) Zero, then DivideByInt;
@@ -1030,10 +1047,46 @@ __global__ void __launch_bounds__(kBlockThreads, FTB_MIN_BLOCKS) render_kernel(c
     constexpr int WARPS = kBlockThreads / 32;
     __shared__ R ring_col[WARPS][kRingSlots][CAP * 3];
     __shared__ int ring_hdr[WARPS][kRingSlots][4];  // out slot of the block's pixel 0, block width, first pixel, pixel count
+    __shared__ R4 origin_tab[kOriginCap];
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
     Counters<STATS> cn;
+
+    // Common-origin bound table.  Most rays start at one of a handful of points: primary rays at the camera, shadow rays
+    // (traced from the fragment towards the light) end at a point light.  For such a ray the object-level bound test
+    // "the line passes within r of the centre and the bound is not behind the origin" is b >= sqrt(|oc|^2 - r^2) with
+    // b = oc . unit(d): the right-hand side depends on (origin, item) only.  Row 0 = camera, row 1 + l = light l (sign
+    // flipped, the ray points at it; a crossing between fragment and light is ahead of the light looking back).
+    // Like the general form the test may keep a miss but never drops a hit.  Rounding budget: (1) b is off by <= 5e-7 |oc|
+    // in FP32 (rsqrt 2 ulp, three products) and the row's |oc|^2 by 2e-7 |oc|^2: covered by the 8e-6 |oc|^2 slack in the
+    // threshold; (2) the traced line does not pass exactly through the common point: a primary ray starts at
+    // fl(camera + 1e-4 d), <= 1e-7 |camera| off, and a shadow ray's rounded direction misses the light by <= 1e-6 tmax.
+    // An offset e changes |oc|^2 - b^2 by <= 2 |oc| |e|, i.e. b >= s - sqrt(2 |oc| |e|) still holds for every hit; with
+    // |oc| bounded by what (1) and the radius inflation do not already cover, that is the per-ray slack passed to
+    // traceScene: 2e-4 |camera| for primary rays, 2e-3 tmax for shadow rays (a crossing between fragment and light has
+    // |oc| <= tmax + r).  -inf = always a candidate (unbounded, or the origin inside the bound).
+    const int n_origins = 1 + S.n_lights;
+    const bool fastBounds = FTB_FAST_BOUNDS != 0 && n_origins * S.n_items <= kOriginCap;
+    const bool fastPrimary = fastBounds && F.mode == 0 && !((FEAT & FT_RNG) != 0 && F.has_focus);
+    if (fastBounds) {
+        for (int o = 0; o < n_origins; ++o) {
+            R4 org;
+            R sign = R(1);
+            if (o == 0) { org.x = F.cam_o[0]; org.y = F.cam_o[1]; org.z = F.cam_o[2]; org.w = R(0); }
+            else { org = ldg4<R>(S.light_a + (o - 1)); sign = R(-1); }
+            for (int j = threadIdx.x; j < S.n_items; j += kBlockThreads) {
+                const R4 bound = ldg4<R>(S.item_bound + j);
+                const Vec<R> v = mk<R>(sign * (bound.x - org.x), sign * (bound.y - org.y), sign * (bound.z - org.z));
+                const R k = dot(v, v) * R(1.0 - 8e-6) - bound.w;
+                R4 row;
+                row.x = v.x; row.y = v.y; row.z = v.z;
+                row.w = (bound.w < R(0) || !(k > R(0))) ? -inf_<R>() : sqrt_(k);
+                origin_tab[o * S.n_items + j] = row;
+            }
+        }
+        __syncthreads();
+    }
     bool overflow = false;
 
     // warp-uniform cursors: the pixel block (or 32 rays) taken from the per-GPU queue, and the unit being dealt from it
@@ -1046,13 +1099,17 @@ __global__ void __launch_bounds__(kBlockThreads, FTB_MIN_BLOCKS) render_kernel(c
     bool exhausted = false;
 
     // per-lane sample / path state
-    int rs = 0, ridx = 0;            // ring slot and position of the sample this lane is tracing
-    int px = 0, py = 0, sj = 0, run_left = 0;  // pixel, sample index within the pixel, samples left in this lane's run
-    unsigned long long sampleIndex = 0;  // index of the sample in the reference's full-frame ray list (RNG key, debug planes)
+    // where this lane's sample is parked, in one register (the kernel is register-bound: every register saved is a spill less):
+    // bits 0..11 = position in the slot, bits 12..15 = ring slot, bits 16.. = samples left in this lane's run
+    int rpos = 0;
+    int px = 0, py = 0, sj = 0;      // pixel, sample index within the pixel
+    // Index of the sample in the reference's full-frame ray list (RNG key, debug planes, explicit-ray index).  Variants with
+    // in-path randomness carry it; the others rebuild it from (px, py, sj) in the rare places that want it (two registers).
+    constexpr bool kCarryIndex = (FEAT & FT_RNG) != 0;
+    unsigned long long sampleIndex = 0;
     bool retire = false;             // a sample of this lane finished in the previous iteration (for the unit's count)
     Vec<R> scol = mk<R>(R(0), R(0), R(0));
-    int phase = PH_IDLE, limit = 0;
-    unsigned depth = 0;
+    int phase = PH_IDLE, limit = 0;  // limit: bounces left; the bounce depth (RNG key) is recursion_limit - limit
     R weight = R(1), tmax = R(0);
     Ray<R> ray;            // the ray to trace next: path ray (un-offset) in PH_NEAREST, shadow ray in PH_SHADOW
     Vec<R> pathD;          // direction of the current path ray (viewRay.d of the fragment being shaded)
@@ -1074,7 +1131,7 @@ __global__ void __launch_bounds__(kBlockThreads, FTB_MIN_BLOCKS) render_kernel(c
             unsigned doneSlots = 0;
 #pragma unroll
             for (int k = 0; k < kRingSlots; ++k) {
-                remaining[k] -= __popc(__ballot_sync(full, retire && rs == k));
+                remaining[k] -= __popc(__ballot_sync(full, retire && ((rpos >> 12) & 0xf) == k));
                 if (busy[k] && remaining[k] == 0) { doneSlots |= 1u << k; busy[k] = false; }
             }
             while (doneSlots) {  // rare relative to the trace: one out-of-line copy keeps the hot loop small
@@ -1108,8 +1165,9 @@ __global__ void __launch_bounds__(kBlockThreads, FTB_MIN_BLOCKS) render_kernel(c
                         const int ltile = F.tile_order ? __ldg(F.tile_order + tpos) : tpos;  // costliest tiles first
                         const int tile = ltile * F.shard_count + F.shard_index;
                         const int sx = (sub & ((1 << bpr_log) - 1)) << F.bw_log, sy = (sub >> bpr_log) << F.bh_log;
-                        blk_x0 = (tile % F.tiles_x) * FTB_TILE_W + sx;
-                        blk_y0 = (tile / F.tiles_x) * FTB_TILE_H + sy;
+                        const int tile_y = F.tiles_x_magic ? (int)__umulhi((unsigned)tile, F.tiles_x_magic) : tile / F.tiles_x;
+                        blk_x0 = (tile - tile_y * F.tiles_x) * FTB_TILE_W + sx;
+                        blk_y0 = tile_y * FTB_TILE_H + sy;
                         blk_slot0 = ltile * FTB_TILE_PIXELS + sy * FTB_TILE_W + sx;
                         blk_w = max(1, min(1 << F.bw_log, F.gw - blk_x0));
                         blk_npix = max(0, min(1 << F.bw_log, F.gw - blk_x0)) * max(0, min(1 << F.bh_log, F.gh - blk_y0));
@@ -1137,13 +1195,14 @@ __global__ void __launch_bounds__(kBlockThreads, FTB_MIN_BLOCKS) render_kernel(c
                 const int pu = rpp == 1 ? q : (int)__umulhi((unsigned)q, F.rpp_magic);  // pixel within the unit = q / rpp
                 const int pj = u_p0 + pu;                                        // pixel within the block
                 sj = F.s_base + (q - pu * rpp) * run;
-                rs = u_slot; ridx = q * run; run_left = run;
+                rpos = (q * run) | (u_slot << 12) | (run << 16);
                 if (F.mode == 0) {
                     const int ly = blk_w == 8 ? (pj >> 3) : pj / blk_w;
                     px = blk_x0 + (pj - ly * blk_w); py = blk_y0 + ly;
-                    sampleIndex = ((unsigned long long)py * (unsigned)F.gw + (unsigned)px) * (unsigned)spp + (unsigned)sj;
+                    if constexpr (kCarryIndex) sampleIndex = ((unsigned long long)py * (unsigned)F.gw + (unsigned)px) * (unsigned)spp + (unsigned)sj;
                 } else {
-                    sampleIndex = (unsigned long long)blk_slot0 + (unsigned)pj;
+                    px = blk_slot0 + pj; py = 0;  // the ray's index
+                    if constexpr (kCarryIndex) sampleIndex = (unsigned long long)(unsigned)px;
                 }
                 phase = PH_START;
                 need = false;
@@ -1154,11 +1213,11 @@ __global__ void __launch_bounds__(kBlockThreads, FTB_MIN_BLOCKS) render_kernel(c
         if (phase == PH_START) {  // a new sample: dealt just now, or the next one of this lane's run
             if (F.mode == 0) ray = primaryRay<R, FEAT>(F, px, py, sj, sampleIndex);
             else {
-                const double* q = F.rays + 6 * sampleIndex;
+                const double* q = F.rays + 6 * (size_t)(unsigned)px;
                 ray.o = mk<R>((R)__ldg(q), (R)__ldg(q + 1), (R)__ldg(q + 2));
                 ray.d = mk<R>((R)__ldg(q + 3), (R)__ldg(q + 4), (R)__ldg(q + 5));
             }
-            phase = PH_NEAREST; depth = 0; limit = F.recursion_limit; weight = R(1);
+            phase = PH_NEAREST; limit = F.recursion_limit; weight = R(1);
             scol = mk<R>(R(0), R(0), R(0));
             cn.add(ST_PRIMARY);
         }
@@ -1171,6 +1230,12 @@ __global__ void __launch_bounds__(kBlockThreads, FTB_MIN_BLOCKS) render_kernel(c
         // Measured: -28 % on the full-size mesh, -12 % house, -8 % night-house, -5 % moon, +-0 cfg2.
         bool hold = false;
         if constexpr (FTB_PHASE_ALIGN != 0) hold = __any_sync(full, phase == PH_SHADOW) && phase == PH_NEAREST;
+        // all lanes that trace in this iteration have a row in the common-origin table?  (warp-uniform)
+        bool tabled = false;
+        if (fastBounds) {
+            const bool mine = phase == PH_NEAREST ? (fastPrimary && limit == F.recursion_limit) : tmax < realmax_<R>();  // finite tmax: a point light
+            tabled = !__any_sync(full, phase != PH_IDLE && !hold && !mine);
+        }
         if (phase == PH_IDLE || hold) continue;
 
         // ---- trace this lane's current ray: the one expensive step ------------------------------------------------
@@ -1185,15 +1250,17 @@ __global__ void __launch_bounds__(kBlockThreads, FTB_MIN_BLOCKS) render_kernel(c
         // on t = 0 or beyond and the plane reflects / shadows itself.  Such rays skip that one leaf; nothing else changes.
         int skipLeaf = -1;
         if constexpr (sizeof(R) == 4 && (FEAT & FT_PLANAR) != 0) {  // `f` is still the fragment this bounce / shadow ray starts from
-            if (f.planarLeaf >= 0 && (phase == PH_NEAREST ? depth > 0 : dot(ray.d, f.n) >= R(0))) skipLeaf = f.planarLeaf;
+            if (f.planarLeaf >= 0 && (phase == PH_NEAREST ? limit < F.recursion_limit : dot(ray.d, f.n) >= R(0))) skipLeaf = f.planarLeaf;
         }
-        const HitInfo<R> h = traceScene<R, FEAT, STATS>(S, tr, phase == PH_NEAREST ? inf_<R>() : tmax, phase == PH_SHADOW, skipLeaf, overflow, cn);
+        const HitInfo<R> h = traceScene<R, FEAT, STATS>(S, tr, phase == PH_NEAREST ? inf_<R>() : tmax, phase == PH_SHADOW, skipLeaf,
+                                                        tabled ? origin_tab + (phase == PH_NEAREST ? 0 : 1 + li) * S.n_items : nullptr,
+                                                        phase == PH_NEAREST ? F.primary_slack : R(2e-3) * tmax, overflow, cn);
 
         // ---- consume the result -----------------------------------------------------------------------------------------
         bool got = false;       // an intensity for light `li` is ready
         R intensity = R(0);
         if (phase == PH_NEAREST) {
-            if (depth == 0 && F.dbg_prim) {
+            if (limit == F.recursion_limit && F.dbg_prim) {
                 int prim = -1, sub = 0;
                 if (h.leaf >= 0) {
                     const int4 meta = __ldg(S.leaf_meta + h.leaf);
@@ -1201,15 +1268,18 @@ __global__ void __launch_bounds__(kBlockThreads, FTB_MIN_BLOCKS) render_kernel(c
                     prim = meta.z;
                     sub = (kind == LEAF_CUBE || kind == LEAF_MESH) ? h.sub : ((kind == LEAF_TRIANGLE) ? 0 : meta.w);
                 }
-                F.dbg_prim[sampleIndex] = prim;
-                if (F.dbg_sub) F.dbg_sub[sampleIndex] = sub;
-                if (F.dbg_t) F.dbg_t[sampleIndex] = h.leaf >= 0 ? (double)h.t : -1.0;
+                const unsigned long long at = F.mode == 0 ? ((unsigned long long)py * (unsigned)F.gw + (unsigned)px) * (unsigned)spp + (unsigned)sj
+                                                          : (unsigned long long)(unsigned)px;
+                F.dbg_prim[at] = prim;
+                if (F.dbg_sub) F.dbg_sub[at] = sub;
+                if (F.dbg_t) F.dbg_t[at] = h.leaf >= 0 ? (double)h.t : -1.0;
             }
             if (h.leaf < 0 || S.n_lights <= 0) {  // miss: empty sum (Shading.fs:137-139)
-                R* c = &ring_col[wib][rs][3 * ridx];
+                R* c = &ring_col[wib][0][3 * (((rpos >> 12) & 0xf) * CAP + (rpos & 0xfff))];
                 c[0] = scol.x; c[1] = scol.y; c[2] = scol.z;
                 retire = true;
-                if (--run_left > 0) { ++ridx; ++sj; ++sampleIndex; phase = PH_START; } else phase = PH_IDLE;
+                rpos -= 0xffff;  // one sample fewer in the run, one position further
+                if ((rpos >> 16) > 0) { ++sj; if constexpr (kCarryIndex) ++sampleIndex; phase = PH_START; } else phase = PH_IDLE;
                 continue;
             }
             cn.add(ST_SHADED);
@@ -1226,7 +1296,7 @@ __global__ void __launch_bounds__(kBlockThreads, FTB_MIN_BLOCKS) render_kernel(c
                     ++sk;
                     if (sk < lk.y) {
                         const R4 la = ldg4<R>(S.light_a + li);
-                        ray.d = jitterVector<R>(F.seed, sampleIndex, depth, (unsigned)li, (unsigned)sk, la.w, -mk<R>(la.x, la.y, la.z));
+                        ray.d = jitterVector<R>(F.seed, sampleIndex, (unsigned)(F.recursion_limit - limit), (unsigned)li, (unsigned)sk, la.w, -mk<R>(la.x, la.y, la.z));
                         continue;  // next sample of the same light
                     }
                     intensity = (R)(lk.y - occluded) / (R)lk.y;
@@ -1260,7 +1330,7 @@ __global__ void __launch_bounds__(kBlockThreads, FTB_MIN_BLOCKS) render_kernel(c
                 if constexpr ((FEAT & FT_RNG) != 0) {
                     sk = 0; occluded = 0;
                     tmax = realmax_<R>();
-                    ray.d = jitterVector<R>(F.seed, sampleIndex, depth, (unsigned)li, 0u, la.w, -lv);
+                    ray.d = jitterVector<R>(F.seed, sampleIndex, (unsigned)(F.recursion_limit - limit), (unsigned)li, 0u, la.w, -lv);
                 }
             } else {
                 tmax = realmax_<R>();
@@ -1276,14 +1346,15 @@ __global__ void __launch_bounds__(kBlockThreads, FTB_MIN_BLOCKS) render_kernel(c
         if (f.applyLighting && f.reflectance > R(0) && limit > 0) {
             weight = weight * ((R)S.n_lights * f.reflectance);
             ray.o = f.p; ray.d = reflect(f.n, pathD);
-            --limit; ++depth;
+            --limit;
             phase = PH_NEAREST;
             cn.add(ST_REFLECTION);
         } else {  // the sample is complete: park its colour in the unit's slot; take the next sample of the run, if any
-            R* c = &ring_col[wib][rs][3 * ridx];
+            R* c = &ring_col[wib][0][3 * (((rpos >> 12) & 0xf) * CAP + (rpos & 0xfff))];
             c[0] = scol.x; c[1] = scol.y; c[2] = scol.z;
             retire = true;
-            if (--run_left > 0) { ++ridx; ++sj; ++sampleIndex; phase = PH_START; } else phase = PH_IDLE;
+            rpos -= 0xffff;  // one sample fewer in the run, one position further
+            if ((rpos >> 16) > 0) { ++sj; if constexpr (kCarryIndex) ++sampleIndex; phase = PH_START; } else phase = PH_IDLE;
         }
     }
     if (overflow) atomicExch(F.overflow, 1u);
