@@ -88,6 +88,7 @@ __global__ void widen_kernel(const R* in, double* out, long long n)
 }  // namespace ftb
 
 namespace ftb {
+static_assert((unsigned)FT_TABLE == kFeatOriginTable, "lower.h and device_scene.h disagree on the table feature bit");
 // kernel variants compiled by the Makefile (render_variant.cu), listed through -DFTB_FEAT_LIST_F32 / _F64
 #define X(feat) cudaError_t launch_f32_##feat(const DevScene<float>&, const DevFrame<float>&, bool, int, cudaStream_t, int*);
 FTB_FEAT_LIST_F32
@@ -111,7 +112,7 @@ template <> struct VariantTable<double> { static const Variant<double>* begin() 
 
 // the smallest compiled variant that covers `need` (and has the counting kernel if asked for)
 template <typename R>
-const Variant<R>* pickVariant(unsigned need, bool stats)
+const Variant<R>* pickCover(unsigned need, bool stats)
 {
     const Variant<R>* best = nullptr;
     for (int i = 0; i < VariantTable<R>::size(); ++i) {
@@ -120,6 +121,18 @@ const Variant<R>* pickVariant(unsigned need, bool stats)
         if (!best || __builtin_popcount(v->feat) < __builtin_popcount(best->feat)) best = v;
     }
     return best;
+}
+// FT_TABLE is an optimisation, not a requirement: a scene that would like the common-origin bound table but whose other
+// needs are only covered together with it by the generic kernel runs on the specialised kernel without the table.
+template <typename R>
+const Variant<R>* pickVariant(unsigned need, bool stats)
+{
+    const Variant<R>* v = pickCover<R>(need, stats);
+    if ((need & FT_TABLE) && (!v || v->feat == FT_ALL)) {
+        const Variant<R>* w = pickCover<R>(need & ~(unsigned)FT_TABLE, stats);
+        if (w && w->feat != FT_ALL) return w;
+    }
+    return v;
 }
 }  // namespace ftb
 

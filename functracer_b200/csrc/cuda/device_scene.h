@@ -42,7 +42,8 @@ enum Feature : unsigned {
     FT_RNG = 0x40,    // soft directional lights, depth of field
     FT_CSGN = 0x80,   // any other CSG item (general post-order program, inlined)
     FT_PLANAR = 0x100,  // a top-level plane / square / circle leaf exists (FP32 self-intersection guard, render.cuh)
-    FT_ALL = 0x1ff
+    FT_TABLE = 0x200,  // enough top-level items for the common-origin bound table to pay (lower.h kFeatOriginTable, render.cuh)
+    FT_ALL = 0x3ff
 };
 
 enum StatSlot : int {

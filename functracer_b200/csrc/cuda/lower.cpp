@@ -625,6 +625,7 @@ int lower_scene(const ftb_scene_desc& d, Lowered& out, std::string& err)
     if (out.has_soft_light) f |= 0x40;
     for (const Leaf& lf : out.leaves)
         if (lf.top_level && (lf.kind == LEAF_PLANE || lf.kind == LEAF_SQUARE || lf.kind == LEAF_CIRCLE)) f |= 0x100;
+    if (wantsOriginTable((int)out.items.size(), d.n_lights)) f |= kFeatOriginTable;
     out.features = f;
     if (out.has_mesh) buildMeshIndex(d, out);
     return FTB_OK;

@@ -22,6 +22,13 @@
 
 namespace ftb {
 
+// The common-origin bound table (render.cuh) is used when the item list is long enough to matter and the table fits;
+// such scenes carry the feature bit 0x200 (device_scene.h FT_TABLE).
+constexpr int kOriginCap = 256;     // rows x items (4 KB of shared memory in FP32)
+constexpr int kOriginMinItems = 8;
+constexpr unsigned kFeatOriginTable = 0x200;
+inline bool wantsOriginTable(int n_items, int n_lights) { return n_items >= kOriginMinItems && (1 + n_lights) * n_items <= kOriginCap; }
+
 enum LeafKind : int32_t {
     LEAF_SPHERE = 0,
     LEAF_PLANE = 1,

@@ -1016,7 +1016,6 @@ constexpr int kRingSlots = FTB_RING_SLOTS;
 #ifndef FTB_FAST_BOUNDS
 #define FTB_FAST_BOUNDS 1
 #endif
-constexpr int kOriginCap = 256;  // rows x items of the common-origin bound table (4 KB of shared memory in FP32)
 
 // Folds a completed unit: every pixel's samples of this pass, in sample order, onto the running sum of the earlier
 // passes; the last pass divides by the frame's sample count (Array.average = fold (+) Zero, then DivideByInt;
@@ -1047,7 +1046,8 @@ __global__ void __launch_bounds__(kBlockThreads, FTB_MIN_BLOCKS) render_kernel(c
     constexpr int WARPS = kBlockThreads / 32;
     __shared__ R ring_col[WARPS][kRingSlots][CAP * 3];
     __shared__ int ring_hdr[WARPS][kRingSlots][4];  // out slot of the block's pixel 0, block width, first pixel, pixel count
-    __shared__ R4 origin_tab[kOriginCap];
+    constexpr bool kTable = FTB_FAST_BOUNDS != 0 && (FEAT & FT_TABLE) != 0;
+    __shared__ R4 origin_tab[kTable ? kOriginCap : 1];
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -1067,7 +1067,7 @@ __global__ void __launch_bounds__(kBlockThreads, FTB_MIN_BLOCKS) render_kernel(c
     // traceScene: 2e-4 |camera| for primary rays, 2e-3 tmax for shadow rays (a crossing between fragment and light has
     // |oc| <= tmax + r).  -inf = always a candidate (unbounded, or the origin inside the bound).
     const int n_origins = 1 + S.n_lights;
-    const bool fastBounds = FTB_FAST_BOUNDS != 0 && n_origins * S.n_items <= kOriginCap;
+    const bool fastBounds = kTable && S.n_items >= kOriginMinItems && n_origins * S.n_items <= kOriginCap;  // = wantsOriginTable
     const bool fastPrimary = fastBounds && F.mode == 0 && !((FEAT & FT_RNG) != 0 && F.has_focus);
     if (fastBounds) {
         for (int o = 0; o < n_origins; ++o) {
