@@ -247,7 +247,7 @@ typedef struct ftb_stats {
     uint64_t bsp_nodes_visited; /* nodes of the device's mesh index (a BVH over the BSP's triangles) visited */
     uint64_t bound_tests;     /* object-level bound tests (no counterpart in the reference) */
     uint64_t csg_ops;
-    double flops;             /* algorithmic flops by the SURVEY.md 8(d) table (+ 17 per bound test) */
+    double flops;             /* algorithmic flops by the SURVEY.md 8(d) table (+ 17 per bound test, 5 when answered from the common-origin table) */
     double kernel_ms;         /* device time of the render kernel(s) */
     double total_ms;          /* wall time of the call */
     int32_t kernel_launches;
