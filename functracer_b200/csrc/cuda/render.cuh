@@ -1058,14 +1058,15 @@ __global__ void __launch_bounds__(kBlockThreads, FTB_MIN_BLOCKS) render_kernel(c
     // "the line passes within r of the centre and the bound is not behind the origin" is b >= sqrt(|oc|^2 - r^2) with
     // b = oc . unit(d): the right-hand side depends on (origin, item) only.  Row 0 = camera, row 1 + l = light l (sign
     // flipped, the ray points at it; a crossing between fragment and light is ahead of the light looking back).
-    // Like the general form the test may keep a miss but never drops a hit.  Rounding budget: (1) b is off by <= 5e-7 |oc|
-    // in FP32 (rsqrt 2 ulp, three products) and the row's |oc|^2 by 2e-7 |oc|^2: covered by the 8e-6 |oc|^2 slack in the
-    // threshold; (2) the traced line does not pass exactly through the common point: a primary ray starts at
-    // fl(camera + 1e-4 d), <= 1e-7 |camera| off, and a shadow ray's rounded direction misses the light by <= 1e-6 tmax.
-    // An offset e changes |oc|^2 - b^2 by <= 2 |oc| |e|, i.e. b >= s - sqrt(2 |oc| |e|) still holds for every hit; with
-    // |oc| bounded by what (1) and the radius inflation do not already cover, that is the per-ray slack passed to
-    // traceScene: 2e-4 |camera| for primary rays, 2e-3 tmax for shadow rays (a crossing between fragment and light has
-    // |oc| <= tmax + r).  -inf = always a candidate (unbounded, or the origin inside the bound).
+    // Like the general form the test may keep a miss but never drops a hit.  Rounding budget (tests/test_bound_table_budget.py
+    // replays it in float32 against exact geometry): (1) b is off by <= 5e-7 |oc| in FP32 (rsqrt 2 ulp, three products) and
+    // the row's |oc|^2 by 2e-7 |oc|^2: 1.2e-6 of the 8e-6 |oc|^2 slack in the threshold.  (2) The traced line does not pass
+    // exactly through the common point: a primary ray starts at fl(camera + 1e-4 d), g <= 1e-7 |camera| off the ideal line;
+    // a shadow ray's rounded direction (fl(L - P) normalised, 1.7e-7 rad) misses the light by g <= 1e-6 tmax (6x margin).
+    // An offset g changes |oc|^2 - b^2 by <= 2 |oc| g + g^2, of which the remaining 7e-6 |oc|^2 of the threshold slack
+    // absorbs all but 2 |oc| g - 7e-6 |oc|^2 <= g^2 / 7e-6 (maximum over |oc|): adding slack = sqrt(g^2 / 7e-6) = 378 g to b
+    // covers it for every item.  That per-ray slack is 2e-4 |camera| for primary rays (5x margin) and 4e-4 tmax for
+    // shadow rays.  -inf = always a candidate (unbounded, or the origin inside the bound).
     const int n_origins = 1 + S.n_lights;
     const bool fastBounds = kTable && S.n_items >= kOriginMinItems && n_origins * S.n_items <= kOriginCap;  // = wantsOriginTable
     const bool fastPrimary = fastBounds && F.mode == 0 && !((FEAT & FT_RNG) != 0 && F.has_focus);
@@ -1254,7 +1255,7 @@ __global__ void __launch_bounds__(kBlockThreads, FTB_MIN_BLOCKS) render_kernel(c
         }
         const HitInfo<R> h = traceScene<R, FEAT, STATS>(S, tr, phase == PH_NEAREST ? inf_<R>() : tmax, phase == PH_SHADOW, skipLeaf,
                                                         tabled ? origin_tab + (phase == PH_NEAREST ? 0 : 1 + li) * S.n_items : nullptr,
-                                                        phase == PH_NEAREST ? F.primary_slack : R(2e-3) * tmax, overflow, cn);
+                                                        phase == PH_NEAREST ? F.primary_slack : R(4e-4) * tmax, overflow, cn);
 
         // ---- consume the result -----------------------------------------------------------------------------------------
         bool got = false;       // an intensity for light `li` is ready
