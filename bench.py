@@ -51,6 +51,11 @@ def _peaks():
     return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
 
 
+# per-ray intersection cost of the reference's brute-force algorithm on the bundled scenes (flop table)
+_BRUTE_FORCE_FLOPS_PER_RAY = {"sample": 366, "hollow_sphere": 2972, "house": 610, "night_house": 1285, "repeat": 1214, "moon": 244,
+                              "bunny": 960 * 45 + 33}
+
+
 def _fp32_peak_tflops():
     """FP32 pipe peak.  Prefers the on-box FMA-saturation measurement committed under profiles/
     (tools/fp32_peak.cu); else 148 SM x 128 lanes x 2 x clocks.max.sm from MEASURED_PEAKS.json."""
@@ -378,12 +383,19 @@ def main():
                     "scene_create_ms_first_call_incl_cuda_init": create_ms},
             "gpu_launches": int(args.steps * (2 if world == 1 else (2 if rank == 0 else 1))),
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": _traffic_per_launch(), "kernel": "ftb::render_kernel<float,false>", "kernel_ms": kern_avg_ms,
+                         "traffic": _traffic_per_launch(), "kernel": "ftb::render_kernel<float, FEAT, false> (the scene's feature-specialised variant)", "kernel_ms": kern_avg_ms,
                          "algorithmic_flops_per_launch": local_flops if world == 1 else flops_total / world, "peak_source": peak_how,
                          "hbm_note": "scene is KBs and rays never leave registers; algorithmic HBM bytes = framebuffer only (%d B/launch) vs %s %.0f GB/s"
                                      % (W * H * 12 // world, pk_how, pk.get("hbm_gbs", 0.0))},
             "clocks": clocks,
         }
+        # What the same rays cost with the reference's own algorithm (every leaf tested for every ray):
+        # not the roofline figure -- that counts the tests this kernel performs -- but the size of the algorithmic win.
+        brute = _BRUTE_FORCE_FLOPS_PER_RAY.get(cfg["build"].__name__) if not cfg.get("kw") else None
+        if brute and world == 1:
+            line["roofline"]["reference_algorithm"] = {
+                "intersection_flops_per_ray": brute, "source": "SURVEY.md 8(d): every leaf tested per ray, no culling",
+                "equivalent_tflops": rays_per_frame * brute / (kern_avg_ms * 1e-3) / 1e12}
         if frame_check:
             line["frame_check"] = frame_check
         if not args.no_cpu_baseline:
