@@ -673,6 +673,14 @@ FTB_DEV bool csgPair(const DevScene<R>& S, int leafA, int leafB, int op, const R
     return true;
 }
 
+#ifndef FTB_BOUND_UNROLL
+#define FTB_BOUND_UNROLL 4  // measured: 1, 2 and 8 are slower (the loads and arithmetic of neighbouring items overlap)
+#endif
+#ifndef FTB_TABLE_UNROLL
+#define FTB_TABLE_UNROLL 4
+#endif
+constexpr int kBoundUnroll = FTB_BOUND_UNROLL, kTableUnroll = FTB_TABLE_UNROLL;  // (#pragma unroll takes constants, not macros)
+
 template <typename R>
 struct HitInfo {
     R t;
@@ -701,7 +709,7 @@ FTB_DEV HitInfo<R> traceScene(const DevScene<R>& S, const Ray<R>& wr, R limit, b
         const int n = min(32, S.n_items - base);
         unsigned cand = 0;
         if (tab) {  // rays from a common origin: |oc|, the miss and the behind test fold into one threshold per (origin, item)
-#pragma unroll 4
+#pragma unroll kTableUnroll
             for (int j = 0; j < n; ++j) {
                 const R4 e = tab[base + j];  // xyz = centre - origin (origin - centre for a light: the ray points AT it), w = threshold
                 const R b = e.x * du.x + (e.y * du.y + (e.z * du.z + tabSlack));
@@ -709,7 +717,7 @@ FTB_DEV HitInfo<R> traceScene(const DevScene<R>& S, const Ray<R>& wr, R limit, b
                 cand |= !(b < e.w) ? (1u << j) : 0u;  // NaN stays a candidate, like the general form
             }
         } else {
-#pragma unroll 4
+#pragma unroll kBoundUnroll
             for (int j = 0; j < n; ++j) {
                 const R4 bound = ldg4<R>(S.item_bound + base + j);  // xyz = centre, w = inflated radius^2 (< 0: unbounded)
                 const Vec<R> oc = mk<R>(bound.x - wr.o.x, bound.y - wr.o.y, bound.z - wr.o.z);
@@ -1016,6 +1024,10 @@ constexpr int kRingSlots = FTB_RING_SLOTS;
 #ifndef FTB_FAST_BOUNDS
 #define FTB_FAST_BOUNDS 1
 #endif
+// Experiment switches (tools/ab_build.sh NAME "-DFTB_...=v"): none of them changes a result.
+#ifndef FTB_CURSOR_SMEM
+#define FTB_CURSOR_SMEM 0  // 1: the warp-uniform work cursors live in shared memory between iterations instead of ~15 registers
+#endif
 
 // Folds a completed unit: every pixel's samples of this pass, in sample order, onto the running sum of the earlier
 // passes; the last pass divides by the frame's sample count (Array.average = fold (+) Zero, then DivideByInt;
@@ -1098,6 +1110,31 @@ __global__ void __launch_bounds__(kBlockThreads, FTB_MIN_BLOCKS) render_kernel(c
 #pragma unroll
     for (int k = 0; k < kRingSlots; ++k) { remaining[k] = 0; busy[k] = false; }
     bool exhausted = false;
+#if FTB_CURSOR_SMEM
+    // Experiment: the cursors above are warp-uniform but live in vector registers (they descend from a shuffle); parked in
+    // shared memory between the dealing of one iteration and the fold of the next they free ~15 registers across the trace.
+    // Lane 0 stores, everybody reloads after a warp barrier; the values are the same in every lane by construction.
+    __shared__ int warp_cursor[WARPS][16];
+    auto parkCursors = [&]() {
+        if (lane == 0) {
+            int* w = warp_cursor[wib];
+            w[0] = blk_slot0; w[1] = blk_x0; w[2] = blk_y0; w[3] = blk_w; w[4] = blk_npix; w[5] = blk_pos;
+            w[6] = u_slot; w[7] = u_p0; w[8] = u_pos; w[9] = u_n; w[10] = exhausted ? 1 : 0;
+#pragma unroll
+            for (int k = 0; k < kRingSlots; ++k) { w[11 + 2 * k] = remaining[k]; w[12 + 2 * k] = busy[k] ? 1 : 0; }
+        }
+        __syncwarp();
+    };
+    auto fetchCursors = [&]() {
+        const int* w = warp_cursor[wib];
+        blk_slot0 = w[0]; blk_x0 = w[1]; blk_y0 = w[2]; blk_w = w[3]; blk_npix = w[4]; blk_pos = w[5];
+        u_slot = w[6]; u_p0 = w[7]; u_pos = w[8]; u_n = w[9]; exhausted = w[10] != 0;
+#pragma unroll
+        for (int k = 0; k < kRingSlots; ++k) { remaining[k] = w[11 + 2 * k]; busy[k] = w[12 + 2 * k] != 0; }
+    };
+    static_assert(11 + 2 * kRingSlots <= 16, "warp_cursor row too small");
+    parkCursors();
+#endif
 
     // per-lane sample / path state
     // where this lane's sample is parked, in one register (the kernel is register-bound: every register saved is a spill less):
@@ -1126,6 +1163,9 @@ __global__ void __launch_bounds__(kBlockThreads, FTB_MIN_BLOCKS) render_kernel(c
     const int ppu = max(1, min(32, CAP / scount));    // pixels per unit
 
     for (;;) {
+#if FTB_CURSOR_SMEM
+        fetchCursors();
+#endif
         // ---- fold units whose last sample has landed (colours were parked when each path ended) ---------------------
         if (__any_sync(full, retire)) {
             __syncwarp();  // the parked colours of every lane are visible to the lanes that fold
@@ -1211,6 +1251,9 @@ __global__ void __launch_bounds__(kBlockThreads, FTB_MIN_BLOCKS) render_kernel(c
             u_pos += min(__popc(m), avail);
             m = __ballot_sync(full, need);
         }
+#if FTB_CURSOR_SMEM
+        parkCursors();
+#endif
         if (phase == PH_START) {  // a new sample: dealt just now, or the next one of this lane's run
             if (F.mode == 0) ray = primaryRay<R, FEAT>(F, px, py, sj, sampleIndex);
             else {
