@@ -33,6 +33,14 @@
 #include "device_scene.h"
 #include "lower.h"
 
+// Experiment switches (tools/ab_build.sh NAME "-DFTB_...=v"): none of them changes a result.
+#ifndef FTB_PAIR_NETWORK
+#define FTB_PAIR_NETWORK 0  // 1: two-leaf CSG merges its <= 4 crossings with a 6-exchange network instead of 4 insertions
+#endif
+#ifndef FTB_CURSOR_SMEM
+#define FTB_CURSOR_SMEM 0  // 1: the warp-uniform work cursors live in shared memory between iterations instead of ~15 registers
+#endif
+
 namespace ftb {
 
 #define FTB_DEV __device__ __forceinline__
@@ -642,15 +650,39 @@ FTB_DEV bool csgPair(const DevScene<R>& S, int leafA, int leafB, int op, const R
     intersectLeaf<R, FEAT & ~FT_MESH, STATS>(S, leafB, wr, b, cn);
     if (b.n > 2) return false;
     cn.add(ST_CSG_OPS);
+#if FTB_PAIR_NETWORK
+    // Experiment: the same stable sort as a fixed network.  The four slots (A's hits, then B's, absent ones at +inf and
+    // marked invalid) go through an odd-even transposition network of six compare-exchanges that swap neighbours only
+    // when the later one is strictly smaller, which keeps equal keys in emission order like Seq.sortBy.
+    constexpr unsigned kInvalid = 0xffffffffu;
+    mt[0] = a.n > 0 ? a.t0 : inf_<R>(); mid[0] = a.n > 0 ? ((unsigned)leafA | ((unsigned)(a.s0 & 7) << kIdSubShift)) : kInvalid;
+    mt[1] = a.n > 1 ? a.t1 : inf_<R>(); mid[1] = a.n > 1 ? ((unsigned)leafA | ((unsigned)(a.s1 & 7) << kIdSubShift)) : kInvalid;
+    mt[2] = b.n > 0 ? b.t0 : inf_<R>(); mid[2] = b.n > 0 ? ((unsigned)leafB | ((unsigned)(b.s0 & 7) << kIdSubShift) | kIdSideB) : kInvalid;
+    mt[3] = b.n > 1 ? b.t1 : inf_<R>(); mid[3] = b.n > 1 ? ((unsigned)leafB | ((unsigned)(b.s1 & 7) << kIdSubShift) | kIdSideB) : kInvalid;
+    auto cx = [&](int i, int j) {
+        const bool sw = mt[j] < mt[i];
+        const R ti = mt[i], tj = mt[j];
+        const unsigned ii = mid[i], ij = mid[j];
+        mt[i] = sw ? tj : ti; mt[j] = sw ? ti : tj;
+        mid[i] = sw ? ij : ii; mid[j] = sw ? ii : ij;
+    };
+    cx(0, 1); cx(2, 3); cx(1, 2); cx(0, 1); cx(2, 3); cx(1, 2);
+    mn = 4;
+#else
     if (a.n > 0) insert(a.t0, (unsigned)leafA | ((unsigned)(a.s0 & 7) << kIdSubShift));
     if (a.n > 1) insert(a.t1, (unsigned)leafA | ((unsigned)(a.s1 & 7) << kIdSubShift));
     if (b.n > 0) insert(b.t0, (unsigned)leafB | ((unsigned)(b.s0 & 7) << kIdSubShift) | kIdSideB);
     if (b.n > 1) insert(b.t1, (unsigned)leafB | ((unsigned)(b.s1 & 7) << kIdSubShift) | kIdSideB);
+#endif
     const unsigned rules = csgRuleTable(op);
     bool inA = false, inB = false, decided = false;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
+#if FTB_PAIR_NETWORK
+        if (mid[k] != 0xffffffffu && !decided) {
+#else
         if (k < mn && !decided) {
+#endif
             const unsigned id = mid[k];
             const R ht = mt[k];
             const bool hitB = (id & kIdSideB) != 0;
@@ -1023,10 +1055,6 @@ enum Phase : int { PH_IDLE = 0, PH_NEAREST = 1, PH_SHADOW = 2, PH_START = 3 };
 constexpr int kRingSlots = FTB_RING_SLOTS;
 #ifndef FTB_FAST_BOUNDS
 #define FTB_FAST_BOUNDS 1
-#endif
-// Experiment switches (tools/ab_build.sh NAME "-DFTB_...=v"): none of them changes a result.
-#ifndef FTB_CURSOR_SMEM
-#define FTB_CURSOR_SMEM 0  // 1: the warp-uniform work cursors live in shared memory between iterations instead of ~15 registers
 #endif
 
 // Folds a completed unit: every pixel's samples of this pass, in sample order, onto the running sum of the earlier
