@@ -259,3 +259,39 @@ def test_in_process_multi_gpu_render_matches_single_gpu():
     assert (two["rgb"] == one).all()
     assert counted["stats"].primary_rays == W * H * spp
     assert np.abs(counted["rgb"] - one).max() < 1e-3
+
+
+def _bound_table_scene(n_padding):
+    """A ground plane, six spheres on it (two reflective) and ten small occluders hugging the first of two point lights:
+    17 items, so the kernel answers the bound tests of primary and shadow rays from its common-origin table.  n_padding
+    more spheres 10 000 units BELOW the ground can never be reached by any ray that starts above it, but they make the
+    item list too long for the table (lower.h wantsOriginTable), which switches it off."""
+    rng = np.random.default_rng(5)
+    objs = ["(%s plane)" % scenes._mat((1, 1, 1))]
+    for i in range(6):
+        objs.append("(%s (translate (%g,1,%g) sphere))" % (scenes._mat((0.9, 0.3 + 0.1 * i, 0.2), 0.3 if i % 3 == 0 else 0, 20), -5 + 2 * i, 2 * np.sin(i)))
+    for i in range(10):
+        d = rng.normal(size=3)
+        d /= np.linalg.norm(d)
+        c = np.array([0.0, 6.0, 0.0]) + d * rng.uniform(0.4, 1.5)
+        objs.append("(%s (translate (%g,%g,%g) (scale %g sphere)))" % (scenes._mat((0.2, 0.8, 0.9)), c[0], c[1], c[2], rng.uniform(0.03, 0.2)))
+    for i in range(n_padding):
+        objs.append("(%s (translate (%g,-10000,%g) sphere))" % (scenes._mat((1, 0, 1)), 3.0 * (i % 12), 3.0 * (i // 12)))
+    lights = ["positional pos (0,6,0) falloff (1,0.01,0.02) colour (1,1,1)", "positional pos (40,30,-20) falloff (1,0,0) colour (0.5,0.5,0.5)"]
+    cam = "camera pos (3,4,-12) lookat (0,1,0) up (0,1,0) fov 50 ratio 1"
+    return scenes._options(cam, (256, 192), 2) + "\n".join(objs) + "\n\n" + "\n".join(lights) + "\n"
+
+
+def test_bound_table_cannot_change_a_pixel():
+    """The common-origin bound table is a cull: the same picture must come out with it (17 items) and without it (the same
+    scene padded with unreachable items -- the oracle renders both to the identical frame), and it must match the oracle.
+    The two GPU runs use different kernel variants, whose FP32 results can differ in the last bit, so a handful of
+    silhouette samples may flip; a culled hit would take a whole object or shadow with it."""
+    with_table, without = _bound_table_scene(0), _bound_table_scene(120)
+    ref, got = both(with_table, precision=abi.PRECISION_FP32)
+    check(ref, got, abi.PRECISION_FP32, "bound-table", within=0.998)
+    _, got2 = both(without, precision=abi.PRECISION_FP32)
+    prim_diff = float((got["prim"] != got2["prim"]).mean())
+    rgb_diff = float((np.abs(got["rgb"] - got2["rgb"]).max(axis=-1) > 1e-4).mean())
+    print("table vs no table: prim mismatch %.2e, pixels off by > 1e-4: %.2e" % (prim_diff, rgb_diff))
+    assert prim_diff <= 1e-4 and rgb_diff <= 2e-4
