@@ -37,6 +37,9 @@
 #ifndef FTB_PAIR_NETWORK
 #define FTB_PAIR_NETWORK 0  // 1: two-leaf CSG merges its <= 4 crossings with a 6-exchange network instead of 4 insertions
 #endif
+#ifndef FTB_CUBE_BRANCHFREE
+#define FTB_CUBE_BRANCHFREE 0  // 1: cube faces and their sink updates as selects instead of branches
+#endif
 #ifndef FTB_CURSOR_SMEM
 #define FTB_CURSOR_SMEM 0  // 1: the warp-uniform work cursors live in shared memory between iterations instead of ~15 registers
 #endif
@@ -389,6 +392,19 @@ FTB_DEV void intersectLeaf(const DevScene<R>& S, int leaf, const Ray<R>& wr, Sin
             // bottom/top: w = y, (a,b) = (x,z); left/right: w = x, (a,b) = (y,z); front/back: w = z, (a,b) = (x,y).
             // num/denom signs follow each square's own frame (DESIGN.md "cube"): bottom/top: num = k - w, denom = +wd;
             // left/right/front/back (rotated frames): num = w - k, denom = -wd.
+#if FTB_CUBE_BRANCHFREE
+            // Experiment: the six faces as straight-line code (selects instead of the two branches per face): the taken
+            // branches of this block are where the cfg2 kernel waits for instruction fetch.  Same arithmetic, same order.
+#define FTB_CUBE_FACE(face, wo, wd, ao, ad, bo, bd, k, rotated)                                   \
+            {                                                                                         \
+                const R num = (rotated) ? ((wo) - R(k)) : (R(k) - (wo));                              \
+                const R denom = (rotated) ? -(wd) : (wd);                                             \
+                const bool par = abs_(denom) < eps;                                                   \
+                const R t = par ? R(0) : num / denom;                                                 \
+                const R pa = (ao) + t * (ad), pb = (bo) + t * (bd);                                   \
+                sink.hitIf((!par || num < eps) && (pa >= R(0)) && (pa <= R(1)) && (pb >= R(0)) && (pb <= R(1)), t, face); \
+            }
+#else
 #define FTB_CUBE_FACE(face, wo, wd, ao, ad, bo, bd, k, rotated)                                   \
             {                                                                                         \
                 R num = (rotated) ? ((wo) - R(k)) : (R(k) - (wo));                                    \
@@ -401,6 +417,7 @@ FTB_DEV void intersectLeaf(const DevScene<R>& S, int leaf, const Ray<R>& wr, Sin
                     if ((pa >= R(0)) && (pa <= R(1)) && (pb >= R(0)) && (pb <= R(1))) sink.hit(t, face); \
                 }                                                                                     \
             }
+#endif
             FTB_CUBE_FACE(0, oy, r.d.y, ox, r.d.x, oz, r.d.z, 0, false)
             FTB_CUBE_FACE(1, oy, r.d.y, ox, r.d.x, oz, r.d.z, 1, false)
             FTB_CUBE_FACE(2, ox, r.d.x, oy, r.d.y, oz, r.d.z, 0, true)
@@ -476,6 +493,11 @@ struct RaySink {
     {
         if (ht >= R(0) && ht < limit) { limit = ht; leaf = cur; sub = hsub; flip = 0; }
     }
+    FTB_DEV void hitIf(bool valid, R ht, int hsub)  // the same, as selects (no branch)
+    {
+        const bool take = valid && ht >= R(0) && ht < limit;
+        limit = take ? ht : limit; leaf = take ? cur : leaf; sub = take ? hsub : sub; flip = take ? 0 : flip;
+    }
     FTB_DEV bool done() const { return any && leaf >= 0; }
 };
 // CSG operand: append to the per-ray hit stack.
@@ -497,6 +519,7 @@ struct ListSink {
         if (top < kHitCap) { stack[top].t = ht; stack[top].id = (unsigned)cur | ((unsigned)(hsub & 7) << kIdSubShift); ++top; }
         else overflow = true;
     }
+    FTB_DEV void hitIf(bool valid, R ht, int hsub) { if (valid) hit(ht, hsub); }
     FTB_DEV bool done() const { return false; }
 };
 
@@ -616,6 +639,13 @@ struct PairSink {
     {
         if (n == 0) { t0 = ht; s0 = hsub; } else if (n == 1) { t1 = ht; s1 = hsub; }
         ++n;
+    }
+    FTB_DEV void hitIf(bool valid, R ht, int hsub)  // the same, as selects (no branch)
+    {
+        const bool first = valid && n == 0, second = valid && n == 1;
+        t0 = first ? ht : t0; s0 = first ? hsub : s0;
+        t1 = second ? ht : t1; s1 = second ? hsub : s1;
+        n += valid ? 1 : 0;
     }
     FTB_DEV bool done() const { return false; }
 };
