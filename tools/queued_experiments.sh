@@ -1,0 +1,26 @@
+#!/bin/bash
+# The experiments DESIGN.md §8 lists as "built but not yet measured", as two steps:
+#   tools/queued_experiments.sh build        (here, no GPU: builds ab/libftb_{cursor,net,cubebf,all3}.so, prints SASS sizes / spills)
+#   gpurun --timeout 1500 -- 'bash tools/queued_experiments.sh run 2>&1 | tee gpurun_out/queued.log'
+# "run" first checks every library against the oracle (the FP32 / FP64 parity tests and the fuzz scenes go through
+# FTB_LIB), then prints same-box timings next to the in-tree build.  A switch is adopted only if parity is green and it
+# wins on the workloads it targets without losing > 1 % elsewhere (box-to-box variance is 1-2 %: compare within one run).
+set -e
+cd "$(dirname "$0")/.."
+LIBS="cursor net cubebf all3"
+case "$1" in
+build)
+  bash tools/ab_build.sh cursor "-DFTB_CURSOR_SMEM=1"
+  bash tools/ab_build.sh net    "-DFTB_PAIR_NETWORK=1"
+  bash tools/ab_build.sh cubebf "-DFTB_CUBE_BRANCHFREE=1"
+  bash tools/ab_build.sh all3   "-DFTB_CURSOR_SMEM=1 -DFTB_PAIR_NETWORK=1 -DFTB_CUBE_BRANCHFREE=1"
+  ;;
+run)
+  for lib in $LIBS; do
+    echo "== parity with ab/libftb_$lib.so"
+    FTB_LIB=$PWD/ab/libftb_$lib.so timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_fuzz.py tests/test_golden.py -m gpu -x -q 2>&1 | tail -n 2
+  done
+  bash tools/ab_bench.sh "cfg2-hollow-sphere cfg3-house cfg3-night-house cfg4-bunny-full-d14 cfg5-moon cfg5-repeat" "tree $LIBS"
+  ;;
+*) echo "usage: $0 build|run"; exit 2;;
+esac
