@@ -40,6 +40,9 @@
 #ifndef FTB_CUBE_BRANCHFREE
 #define FTB_CUBE_BRANCHFREE 0  // 1: cube faces and their sink updates as selects instead of branches
 #endif
+#ifndef FTB_TABLE_TIGHT_SLACK
+#define FTB_TABLE_TIGHT_SLACK 0  // 1: the per-ray slack of the bound table only covers what the bounds' own inflation does not
+#endif
 #ifndef FTB_CURSOR_SMEM
 #define FTB_CURSOR_SMEM 0  // 1: the warp-uniform work cursors live in shared memory between iterations instead of ~15 registers
 #endif
@@ -1129,14 +1132,15 @@ __global__ void __launch_bounds__(kBlockThreads, FTB_MIN_BLOCKS) render_kernel(c
     // b = oc . unit(d): the right-hand side depends on (origin, item) only.  Row 0 = camera, row 1 + l = light l (sign
     // flipped, the ray points at it; a crossing between fragment and light is ahead of the light looking back).
     // Like the general form the test may keep a miss but never drops a hit.  Rounding budget (tests/test_bound_table_budget.py
-    // replays it in float32 against exact geometry): (1) b is off by <= 5e-7 |oc| in FP32 (rsqrt 2 ulp, three products) and
-    // the row's |oc|^2 by 2e-7 |oc|^2: 1.2e-6 of the 8e-6 |oc|^2 slack in the threshold.  (2) The traced line does not pass
-    // exactly through the common point: a primary ray starts at fl(camera + 1e-4 d), g <= 1e-7 |camera| off the ideal line;
-    // a shadow ray's rounded direction (fl(L - P) normalised, 1.7e-7 rad) misses the light by g <= 1e-6 tmax (6x margin).
-    // An offset g changes |oc|^2 - b^2 by <= 2 |oc| g + g^2, of which the remaining 7e-6 |oc|^2 of the threshold slack
-    // absorbs all but 2 |oc| g - 7e-6 |oc|^2 <= g^2 / 7e-6 (maximum over |oc|): adding slack = sqrt(g^2 / 7e-6) = 378 g to b
-    // covers it for every item.  That per-ray slack is 2e-4 |camera| for primary rays (5x margin) and 4e-4 tmax for
-    // shadow rays.  -inf = always a candidate (unbounded, or the origin inside the bound).
+    // replays it in float32 against exact geometry): (1) in FP32 b is off by <= 4.8e-7 |oc| (rsqrt 2 ulp, three products), the
+    // row's |oc|^2 by 3.6e-7 |oc|^2 and the approximate sqrt moves the threshold by 2 ulp: together < 1.8e-6 |oc|^2 of the
+    // 8e-6 |oc|^2 slack in the threshold.  (2) The traced line does not pass exactly through the common point: a primary ray
+    // starts at fl(camera + 1e-4 d), g <= 1e-7 |camera| off the ideal line; a shadow ray's rounded direction (fl(L - P)
+    // normalised: 1.7e-7 rad) misses the light by g <= 1.7e-7 tmax.  An offset g changes |oc|^2 - b^2 by <= 2 |oc| g + g^2,
+    // of which the remaining 6e-6 |oc|^2 of the threshold slack absorbs all but 2 |oc| g - 6e-6 |oc|^2 <= g^2 / 6e-6 (the
+    // maximum over |oc|): adding sqrt(g^2 / 6e-6) = 410 g to b covers it for every item, i.e. 4.1e-5 |camera| resp.
+    // 7e-5 tmax.  The per-ray slack actually added is 2e-4 |camera| for primary rays and 4e-4 tmax for shadow rays (5x).
+    // -inf = always a candidate (unbounded, or the origin inside the bound).
     const int n_origins = 1 + S.n_lights;
     const bool fastBounds = kTable && S.n_items >= kOriginMinItems && n_origins * S.n_items <= kOriginCap;  // = wantsOriginTable
     const bool fastPrimary = fastBounds && F.mode == 0 && !((FEAT & FT_RNG) != 0 && F.has_focus);
@@ -1158,6 +1162,28 @@ __global__ void __launch_bounds__(kBlockThreads, FTB_MIN_BLOCKS) render_kernel(c
         }
         __syncthreads();
     }
+#if FTB_TABLE_TIGHT_SLACK
+    // Experiment.  A line that misses the common point by g passes at most g further from any centre, and every bound is
+    // already inflated by 0.002 r + 1e-5 (api.cu uploadScene): half of that is kept for the rounding of the leaf
+    // intersectors, the other half, g_allow = 0.001 r_min + 5e-6 with r_min the smallest bounded item, is room for g.  Only
+    // the excess needs the 410x slack derived above; in the bundled scenes there is none (slack 0: a sharper cull).
+    __shared__ R table_k;  // 410 * g_allow
+    if (fastBounds) {
+        __shared__ unsigned min_w_bits;  // smallest inflated r^2 as float bits (non-negative floats order like unsigned ints)
+        if (threadIdx.x == 0) min_w_bits = 0x7f800000u;
+        __syncthreads();
+        for (int j = threadIdx.x; j < S.n_items; j += kBlockThreads) {
+            const float w = (float)ldg4<R>(S.item_bound + j).w;
+            if (w >= 0.0f) atomicMin(&min_w_bits, __float_as_uint(w));
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const R r = max_((sqrt_((R)__uint_as_float(min_w_bits)) * R(1.0 - 1e-6) - R(1e-5)) / R(1.002), R(0));  // undo the inflation, rounding down
+            table_k = R(410) * (R(0.001) * r + R(5e-6));  // +inf when no item is bounded
+        }
+        __syncthreads();
+    }
+#endif
     bool overflow = false;
 
     // warp-uniform cursors: the pixel block (or 32 rays) taken from the per-GPU queue, and the unit being dealt from it
@@ -1356,7 +1382,12 @@ __global__ void __launch_bounds__(kBlockThreads, FTB_MIN_BLOCKS) render_kernel(c
         }
         const HitInfo<R> h = traceScene<R, FEAT, STATS>(S, tr, phase == PH_NEAREST ? inf_<R>() : tmax, phase == PH_SHADOW, skipLeaf,
                                                         tabled ? origin_tab + (phase == PH_NEAREST ? 0 : 1 + li) * S.n_items : nullptr,
-                                                        phase == PH_NEAREST ? F.primary_slack : R(4e-4) * tmax, overflow, cn);
+                                                        #if FTB_TABLE_TIGHT_SLACK
+                                                        max_(R(0), (phase == PH_NEAREST ? F.primary_slack : R(4e-4) * tmax) - table_k),
+#else
+                                                        phase == PH_NEAREST ? F.primary_slack : R(4e-4) * tmax,
+#endif
+                                                        overflow, cn);
 
         // ---- consume the result -----------------------------------------------------------------------------------------
         bool got = false;       // an intensity for light `li` is ready

@@ -11,6 +11,7 @@ the true sphere at an admissible distance must come out as a candidate.  It pins
 table (2e-4 |camera| for primary rays, 4e-4 tmax for shadow rays); no GPU needed.
 """
 import numpy as np
+import pytest
 
 F = np.float32
 N = 400_000
@@ -34,12 +35,14 @@ def _inflated_r2(r):  # api.cu uploadScene: radius inflated by 0.2 % + 1e-5, squ
     return (ri * ri).astype(F)
 
 
-def _row(centre32, origin32, w32, sign):
-    """The table row the kernel's prologue builds (float32)."""
+def _row(centre32, origin32, w32, sign, rng=None):
+    """The table row the kernel's prologue builds (float32); with rng the square root is off by up to 2 ulp like MUFU.SQRT."""
     v = (F(sign) * (centre32 - origin32)).astype(F)
     vv = (v[:, 0] * v[:, 0] + v[:, 1] * v[:, 1] + v[:, 2] * v[:, 2]).astype(F)
     k = (vv * F(1.0 - 8e-6) - w32).astype(F)
     s = np.where((w32 < 0) | ~(k > 0), F(-np.inf), np.sqrt(np.maximum(k, F(0))).astype(F)).astype(F)  # w < 0: unbounded item
+    if rng is not None:
+        s = (s * (F(1) + rng.uniform(-2.4e-7, 2.4e-7, size=s.shape).astype(F))).astype(F)
     return v, s
 
 
@@ -81,20 +84,35 @@ def _true_hit(o, d, c, r, tmin, tmax):
     return hit & (far >= tmin) & (near <= tmax)
 
 
-def test_primary_rays_never_lose_a_hit():
+def _tight(slack32, r):
+    """-DFTB_TABLE_TIGHT_SLACK=1: only the part of the slack that the bound's own inflation (half of 0.002 r + 1e-5, with r
+    the smallest bounded item; here the item itself, the worst case) does not already cover."""
+    return np.maximum(F(0), slack32 - (F(410) * (F(0.001) * r.astype(F) + F(5e-6))).astype(F)).astype(F)
+
+
+@pytest.mark.parametrize("tight", [False, True])
+def test_primary_rays_never_lose_a_hit(tight):
     rng = np.random.default_rng(7)
     cam = (_rand_dirs(rng, N) * 10.0 ** rng.uniform(-1, 3, size=(N, 1))).astype(F)  # |camera| 0.1 .. 1000
     dist = 10.0 ** rng.uniform(-2, 4, size=N)                                        # camera-to-centre 0.01 .. 10 000
     r = dist * 10.0 ** rng.uniform(-3, -0.05, size=N)                                # outside the bound
+    # a third of the cases: bounds so small that their inflation is of the order of the origin's rounding, seen grazing
+    adv = rng.random(N) < 0.33
+    g = 1e-7 * np.linalg.norm(cam.astype(np.float64), axis=1)
+    r_adv = np.maximum((g * 10.0 ** rng.uniform(-1, 1, size=N) - 1e-5) / 0.002, 1e-6)
+    r = np.where(adv & (r_adv < 0.5 * dist), r_adv, r)
     to_c = _rand_dirs(rng, N)
     centre = (cam.astype(np.float64) + to_c * dist[:, None]).astype(F)
     eps = _eps(rng, N)  # aim point: perpendicular offset r (1 + eps) from the centre
+    eps = np.where(adv, rng.uniform(-2e-3, 2e-3, size=N), eps)
     aim = centre.astype(np.float64) + _perp(rng, to_c) * (r * (1 + eps))[:, None]
     d = (_unit(aim - cam.astype(np.float64)) * rng.uniform(0.5, 2.0, size=(N, 1))).astype(F)  # not normalised (Image.fs:83-89)
     o = (cam + F(1e-4) * d).astype(F)                                                # slightOffset (Shading.fs:129)
     w = _inflated_r2(r)
-    v, s = _row(centre, cam, w, +1)
+    v, s = _row(centre, cam, w, +1, rng)
     slack = (F(2e-4) * np.linalg.norm(cam.astype(np.float64), axis=1)).astype(F)
+    if tight:
+        slack = _tight(slack, r)
     cand = _candidate(v, s, _unit32(d, rng), slack)
     truth = _true_hit(o.astype(np.float64), d.astype(np.float64), centre.astype(np.float64), r * 1.001 + 5e-6, 0.0, np.inf)
     assert truth.mean() > 0.3  # the generator does produce hits
@@ -107,7 +125,8 @@ def test_primary_rays_never_lose_a_hit():
     assert clear.sum() > 1000 and (~cand[clear]).mean() > 0.9, (~cand[clear]).mean()
 
 
-def test_point_light_shadow_rays_never_lose_a_hit():
+@pytest.mark.parametrize("tight", [False, True])
+def test_point_light_shadow_rays_never_lose_a_hit(tight):
     rng = np.random.default_rng(11)
     light = (_rand_dirs(rng, N) * 10.0 ** rng.uniform(-1, 3, size=(N, 1))).astype(F)
     tmax_true = 10.0 ** rng.uniform(-2, 4, size=N)                                   # fragment-to-light 0.01 .. 10 000
@@ -121,11 +140,20 @@ def test_point_light_shadow_rays_never_lose_a_hit():
     a = tmax_true * 10.0 ** rng.uniform(-4, 0, size=N)                               # distance from the light along the ray
     r = a * 10.0 ** rng.uniform(-3, -0.05, size=N)                                   # the light is outside the bound
     eps = _eps(rng, N)
+    # a third of the cases: bounds so small that their inflation is of the order of the direction's rounding, seen grazing
+    adv = rng.random(N) < 0.33
+    g = 1.7e-7 * tmax_true
+    r_adv = np.maximum((g * 10.0 ** rng.uniform(-1, 1, size=N) - 1e-5) / 0.002, 1e-6)
+    use = adv & (r_adv < 0.5 * a)
+    r = np.where(use, r_adv, r)
+    eps = np.where(use, rng.uniform(-2e-3, 2e-3, size=N), eps)
     ud = _unit(d.astype(np.float64))
     centre = (light.astype(np.float64) - ud * a[:, None] + _perp(rng, ud) * (r * (1 + eps))[:, None]).astype(F)
     w = _inflated_r2(r)
-    v, s = _row(centre, light, w, -1)
+    v, s = _row(centre, light, w, -1, rng)
     slack = (F(4e-4) * tmax).astype(F)
+    if tight:
+        slack = _tight(slack, r)
     cand = _candidate(v, s, _unit32(d, rng), slack)
     truth = _true_hit(frag.astype(np.float64), d.astype(np.float64), centre.astype(np.float64), r * 1.001 + 5e-6, 0.0, tmax.astype(np.float64) * (1 + 1e-6))
     assert truth.mean() > 0.2

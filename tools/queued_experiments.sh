@@ -1,19 +1,20 @@
 #!/bin/bash
 # The experiments DESIGN.md §8 lists as "built but not yet measured", as two steps:
-#   tools/queued_experiments.sh build        (here, no GPU: builds ab/libftb_{cursor,net,cubebf,all3}.so, prints SASS sizes / spills)
+#   tools/queued_experiments.sh build        (here, no GPU: builds ab/libftb_{cursor,net,cubebf,tight,all4}.so, prints SASS sizes / spills)
 #   gpurun --timeout 1500 -- 'bash tools/queued_experiments.sh run 2>&1 | tee gpurun_out/queued.log'
 # "run" first checks every library against the oracle (the FP32 / FP64 parity tests and the fuzz scenes go through
 # FTB_LIB), then prints same-box timings next to the in-tree build.  A switch is adopted only if parity is green and it
 # wins on the workloads it targets without losing > 1 % elsewhere (box-to-box variance is 1-2 %: compare within one run).
 set -e
 cd "$(dirname "$0")/.."
-LIBS="cursor net cubebf all3"
+LIBS="cursor net cubebf tight all4"
 case "$1" in
 build)
   bash tools/ab_build.sh cursor "-DFTB_CURSOR_SMEM=1"
   bash tools/ab_build.sh net    "-DFTB_PAIR_NETWORK=1"
   bash tools/ab_build.sh cubebf "-DFTB_CUBE_BRANCHFREE=1"
-  bash tools/ab_build.sh all3   "-DFTB_CURSOR_SMEM=1 -DFTB_PAIR_NETWORK=1 -DFTB_CUBE_BRANCHFREE=1"
+  bash tools/ab_build.sh tight  "-DFTB_TABLE_TIGHT_SLACK=1"
+  bash tools/ab_build.sh all4   "-DFTB_CURSOR_SMEM=1 -DFTB_PAIR_NETWORK=1 -DFTB_CUBE_BRANCHFREE=1 -DFTB_TABLE_TIGHT_SLACK=1"
   ;;
 run)
   for lib in $LIBS; do
