@@ -15,6 +15,11 @@ build)
   bash tools/ab_build.sh cubebf "-DFTB_CUBE_BRANCHFREE=1"
   bash tools/ab_build.sh tight  "-DFTB_TABLE_TIGHT_SLACK=1"
   bash tools/ab_build.sh all4   "-DFTB_CURSOR_SMEM=1 -DFTB_PAIR_NETWORK=1 -DFTB_CUBE_BRANCHFREE=1 -DFTB_TABLE_TIGHT_SLACK=1"
+  # mesh frames are bound by the latency of dependent node fetches from L2 (4 % of the rays walk ~90 nodes, tools/bvh_quality.cpp):
+  # more resident warps at the price of spills -- for the mesh workloads only (cfg2 / cfg3 measured slower with 6 and 8)
+  bash tools/ab_build.sh mb6    "-DFTB_MIN_BLOCKS=6"
+  bash tools/ab_build.sh mb8    "-DFTB_MIN_BLOCKS=8"
+  bash tools/ab_build.sh mb6cur "-DFTB_MIN_BLOCKS=6 -DFTB_CURSOR_SMEM=1"
   ;;
 run)
   for lib in $LIBS; do
@@ -22,6 +27,7 @@ run)
     FTB_LIB=$PWD/ab/libftb_$lib.so timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_fuzz.py tests/test_golden.py -m gpu -x -q 2>&1 | tail -n 2
   done
   bash tools/ab_bench.sh "cfg2-hollow-sphere cfg3-house cfg3-night-house cfg4-bunny-full-d14 cfg5-moon cfg5-repeat" "tree $LIBS"
+  bash tools/ab_bench.sh "cfg4-bunny cfg4-bunny-d12 cfg4-bunny-full-d14" "tree mb6 mb8 mb6cur"
   ;;
 *) echo "usage: $0 build|run"; exit 2;;
 esac
