@@ -108,6 +108,7 @@ int main(int argc, char** argv)
         Stat s;
         walk(L, root, lo, hi, area(lo, hi), 0, s);
         long visits = 0, tests = 0, rays = 0, hits = 0, maxVisits = 0;
+        std::vector<int> steps((size_t)W * H, 0);  // node visits + triangle tests of every ray, for the lock-step estimate below
         std::vector<int> stack(256); std::vector<double> stackT(256);
         const double* m = lf.w2m;
         for (int py = 0; py < H; ++py)
@@ -118,7 +119,7 @@ int main(int argc, char** argv)
                 V rd = {m[0] * dw.x + m[1] * dw.y + m[2] * dw.z, m[4] * dw.x + m[5] * dw.y + m[6] * dw.z, m[8] * dw.x + m[9] * dw.y + m[10] * dw.z};
                 V inv = {1 / rd.x, 1 / rd.y, 1 / rd.z};
                 double bt = INFINITY; bool hit = false;
-                int sp = 0, link = root; long v0 = visits;
+                int sp = 0, link = root; long v0 = visits, t0 = tests;
                 for (;;) {
                     while (link >= 0) {
                         ++visits;
@@ -145,7 +146,18 @@ int main(int argc, char** argv)
                     if (link == 0x7fffffff) break;
                 }
                 ++rays; hits += hit; maxVisits = std::max(maxVisits, visits - v0);
+                steps[(size_t)py * W + px] = (int)(visits - v0) + (int)(tests - t0);
             }
+        // a warp traces the 32 pixels of an 8x4 block in lock step: it runs as long as its longest ray
+        long sum = 0, lock = 0;
+        for (int by = 0; by < H; by += 4)
+            for (int bx = 0; bx < W; bx += 8) {
+                int mx = 0;
+                for (int y = by; y < std::min(H, by + 4); ++y)
+                    for (int x = bx; x < std::min(W, bx + 8); ++x) { sum += steps[(size_t)y * W + x]; mx = std::max(mx, steps[(size_t)y * W + x]); }
+                lock += 32L * mx;
+            }
+        std::printf("mesh %d: lock-step efficiency of 8x4 pixel blocks %.1f%% (sum of steps / 32 x longest ray of each block)\n", lf.payload, 100.0 * sum / std::max(1L, lock));
         std::printf("mesh %d: nodes %ld leaves %ld tris/leaf %.2f depth %d SAH %.2f | %dx%d primary rays: hit %.1f%%, nodes/ray %.2f (max %ld), tris/ray %.2f\n",
                     lf.payload, s.nodes, s.leaves, (double)s.tris / std::max(1L, s.leaves), s.depth, s.sah, W, H, 100.0 * hits / rays,
                     (double)visits / rays, maxVisits, (double)tests / rays);
