@@ -1,6 +1,10 @@
 // lower.cpp — see lower.h.
 #include "lower.h"
 
+#ifndef FTB_PAIR_GROUPS
+#define FTB_PAIR_GROUPS 0  // experiment, see render.cuh
+#endif
+
 #include <algorithm>
 #include <array>
 #include <cmath>
@@ -421,6 +425,32 @@ struct Lowerer {
                 it.kind = ITEM_CSG2 | (L.ops[first + 2].kind << 8);
                 it.a = L.ops[first].arg; it.b = L.ops[first + 1].arg;
             }
+#if FTB_PAIR_GROUPS
+            else {
+                // Experiment: an operand may also be a Group of consecutive leaves (solidCylinder = [top; bottom; sides],
+                // Cylinder.fs:25-29): `LEAF l .. LEAF l+k-1, GROUP k`.  The item stays a pair, each operand a run of leaves:
+                // a / b = first leaf | (leaves - 1) << 24.  Every CSG item of the bundled scenes has this shape.
+                auto operand = [&](int& at, int& packed) -> bool {
+                    if (at >= first + count || L.ops[at].kind != OP_LEAF) return false;
+                    const int l0 = L.ops[at].arg;
+                    int k = 1;
+                    while (at + k < first + count && L.ops[at + k].kind == OP_LEAF && L.ops[at + k].arg == l0 + k) ++k;
+                    if (k == 1) { packed = l0; at += 1; return true; }
+                    // a run of k leaves must be closed by GROUP k (else the last leaf belongs to the next operand)
+                    if (at + k < first + count && L.ops[at + k].kind == OP_GROUP && L.ops[at + k].arg == k && k <= 8 && l0 < (1 << 22)) {
+                        packed = l0 | ((k - 1) << 24); at += k + 1; return true;
+                    }
+                    packed = l0; at += 1;
+                    return true;
+                };
+                int at = first, pa = 0, pb = 0;
+                if (operand(at, pa) && operand(at, pb) && at == first + count - 1 && L.ops[at].kind >= OP_UNION) {
+                    Item& it = L.items.back();
+                    it.kind = ITEM_CSG2 | (L.ops[at].kind << 8);
+                    it.a = pa; it.b = pb;
+                }
+            }
+#endif
             return true;
         }
         default: return fail(FTB_ERR_BAD_SCENE, "bad node kind");

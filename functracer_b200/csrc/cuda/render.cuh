@@ -37,6 +37,9 @@
 #ifndef FTB_PAIR_NETWORK
 #define FTB_PAIR_NETWORK 0  // 1: two-leaf CSG merges its <= 4 crossings with a 6-exchange network instead of 4 insertions
 #endif
+#ifndef FTB_PAIR_GROUPS
+#define FTB_PAIR_GROUPS 0  // 1: an operand of the two-leaf CSG fast path may be a Group of consecutive leaves (solidCylinder); also lower.cpp
+#endif
 #ifndef FTB_CUBE_BRANCHFREE
 #define FTB_CUBE_BRANCHFREE 0  // 1: cube faces and their sink updates as selects instead of branches
 #endif
@@ -638,6 +641,21 @@ struct PairSink {
     static constexpr bool kIsRay = false;
     R t0, t1;
     int s0, s1, n;
+#if FTB_PAIR_GROUPS
+    int cur, l0, l1;  // the operand is a run of leaves: which one each crossing belongs to
+    FTB_DEV void hit(R ht, int hsub)
+    {
+        if (n == 0) { t0 = ht; s0 = hsub; l0 = cur; } else if (n == 1) { t1 = ht; s1 = hsub; l1 = cur; }
+        ++n;
+    }
+    FTB_DEV void hitIf(bool valid, R ht, int hsub)
+    {
+        const bool first = valid && n == 0, second = valid && n == 1;
+        t0 = first ? ht : t0; s0 = first ? hsub : s0; l0 = first ? cur : l0;
+        t1 = second ? ht : t1; s1 = second ? hsub : s1; l1 = second ? cur : l1;
+        n += valid ? 1 : 0;
+    }
+#else
     FTB_DEV void hit(R ht, int hsub)
     {
         if (n == 0) { t0 = ht; s0 = hsub; } else if (n == 1) { t1 = ht; s1 = hsub; }
@@ -650,6 +668,7 @@ struct PairSink {
         t1 = second ? ht : t1; s1 = second ? hsub : s1;
         n += valid ? 1 : 0;
     }
+#endif
     FTB_DEV bool done() const { return false; }
 };
 
@@ -678,20 +697,41 @@ FTB_DEV bool csgPair(const DevScene<R>& S, int leafA, int leafB, int op, const R
     PairSink<R> a, b;
     a.n = 0; a.t0 = a.t1 = R(0); a.s0 = a.s1 = 0;
     b.n = 0; b.t0 = b.t1 = R(0); b.s0 = b.s1 = 0;
+#if FTB_PAIR_GROUPS
+    // leafA / leafB = first leaf | (leaves - 1) << 24 (lower.cpp): Group semantics = the leaves' crossings in list order
+    const int firstA = leafA & 0xffffff, endA = firstA + (leafA >> 24) + 1, firstB = leafB & 0xffffff, endB = firstB + (leafB >> 24) + 1;
+    a.cur = a.l0 = a.l1 = firstA;
+    b.cur = b.l0 = b.l1 = firstB;
+    // one copy of the leaf intersectors serves both operands (the variants that need this carry every leaf kind)
+#pragma unroll 1
+    for (int side = 0; side < 2; ++side) {
+        PairSink<R> h;
+        h.n = 0; h.t0 = h.t1 = R(0); h.s0 = h.s1 = 0;
+        const int first = side ? firstB : firstA, end = side ? endB : endA;
+        h.cur = h.l0 = h.l1 = first;
+#pragma unroll 1
+        for (int l = first; l < end; ++l) { h.cur = l; intersectLeaf<R, FEAT & ~FT_MESH, STATS>(S, l, wr, h, cn); }
+        if (h.n > 2) return false;
+        if (side) b = h; else a = h;
+    }
+#define FTB_PAIR_LEAF(sink, k, single) ((unsigned)((k) ? (sink).l1 : (sink).l0))
+#else
     intersectLeaf<R, FEAT & ~FT_MESH, STATS>(S, leafA, wr, a, cn);
     if (a.n > 2) return false;
     intersectLeaf<R, FEAT & ~FT_MESH, STATS>(S, leafB, wr, b, cn);
     if (b.n > 2) return false;
+#define FTB_PAIR_LEAF(sink, k, single) ((unsigned)(single))
+#endif
     cn.add(ST_CSG_OPS);
 #if FTB_PAIR_NETWORK
     // Experiment: the same stable sort as a fixed network.  The four slots (A's hits, then B's, absent ones at +inf and
     // marked invalid) go through an odd-even transposition network of six compare-exchanges that swap neighbours only
     // when the later one is strictly smaller, which keeps equal keys in emission order like Seq.sortBy.
     constexpr unsigned kInvalid = 0xffffffffu;
-    mt[0] = a.n > 0 ? a.t0 : inf_<R>(); mid[0] = a.n > 0 ? ((unsigned)leafA | ((unsigned)(a.s0 & 7) << kIdSubShift)) : kInvalid;
-    mt[1] = a.n > 1 ? a.t1 : inf_<R>(); mid[1] = a.n > 1 ? ((unsigned)leafA | ((unsigned)(a.s1 & 7) << kIdSubShift)) : kInvalid;
-    mt[2] = b.n > 0 ? b.t0 : inf_<R>(); mid[2] = b.n > 0 ? ((unsigned)leafB | ((unsigned)(b.s0 & 7) << kIdSubShift) | kIdSideB) : kInvalid;
-    mt[3] = b.n > 1 ? b.t1 : inf_<R>(); mid[3] = b.n > 1 ? ((unsigned)leafB | ((unsigned)(b.s1 & 7) << kIdSubShift) | kIdSideB) : kInvalid;
+    mt[0] = a.n > 0 ? a.t0 : inf_<R>(); mid[0] = a.n > 0 ? (FTB_PAIR_LEAF(a, 0, leafA) | ((unsigned)(a.s0 & 7) << kIdSubShift)) : kInvalid;
+    mt[1] = a.n > 1 ? a.t1 : inf_<R>(); mid[1] = a.n > 1 ? (FTB_PAIR_LEAF(a, 1, leafA) | ((unsigned)(a.s1 & 7) << kIdSubShift)) : kInvalid;
+    mt[2] = b.n > 0 ? b.t0 : inf_<R>(); mid[2] = b.n > 0 ? (FTB_PAIR_LEAF(b, 0, leafB) | ((unsigned)(b.s0 & 7) << kIdSubShift) | kIdSideB) : kInvalid;
+    mt[3] = b.n > 1 ? b.t1 : inf_<R>(); mid[3] = b.n > 1 ? (FTB_PAIR_LEAF(b, 1, leafB) | ((unsigned)(b.s1 & 7) << kIdSubShift) | kIdSideB) : kInvalid;
     auto cx = [&](int i, int j) {
         const bool sw = mt[j] < mt[i];
         const R ti = mt[i], tj = mt[j];
@@ -702,11 +742,12 @@ FTB_DEV bool csgPair(const DevScene<R>& S, int leafA, int leafB, int op, const R
     cx(0, 1); cx(2, 3); cx(1, 2); cx(0, 1); cx(2, 3); cx(1, 2);
     mn = 4;
 #else
-    if (a.n > 0) insert(a.t0, (unsigned)leafA | ((unsigned)(a.s0 & 7) << kIdSubShift));
-    if (a.n > 1) insert(a.t1, (unsigned)leafA | ((unsigned)(a.s1 & 7) << kIdSubShift));
-    if (b.n > 0) insert(b.t0, (unsigned)leafB | ((unsigned)(b.s0 & 7) << kIdSubShift) | kIdSideB);
-    if (b.n > 1) insert(b.t1, (unsigned)leafB | ((unsigned)(b.s1 & 7) << kIdSubShift) | kIdSideB);
+    if (a.n > 0) insert(a.t0, FTB_PAIR_LEAF(a, 0, leafA) | ((unsigned)(a.s0 & 7) << kIdSubShift));
+    if (a.n > 1) insert(a.t1, FTB_PAIR_LEAF(a, 1, leafA) | ((unsigned)(a.s1 & 7) << kIdSubShift));
+    if (b.n > 0) insert(b.t0, FTB_PAIR_LEAF(b, 0, leafB) | ((unsigned)(b.s0 & 7) << kIdSubShift) | kIdSideB);
+    if (b.n > 1) insert(b.t1, FTB_PAIR_LEAF(b, 1, leafB) | ((unsigned)(b.s1 & 7) << kIdSubShift) | kIdSideB);
 #endif
+#undef FTB_PAIR_LEAF
     const unsigned rules = csgRuleTable(op);
     bool inA = false, inB = false, decided = false;
 #pragma unroll
