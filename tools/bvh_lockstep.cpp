@@ -3,7 +3,9 @@
 // the 32 lanes together, charging every warp-level step its instruction cost whether 1 or 32 lanes take part:
 //   A  the kernel's loop: all lanes descend inner nodes until each has reached a leaf (or run dry), then all test their
 //      leaf's triangles, then pop ("while-while");
-//   B  one loop in which a lane does either one node step or one triangle test per iteration ("if-if").
+//   B  one loop in which a lane does either one node step or one triangle test per iteration ("if-if");
+//   C  loop A fed from a pool: POOL consecutive warps' worth of rays (default 4 x 32) are traversed by one warp whose lanes
+//      fetch the next pooled ray the moment their own ends (what a per-warp ray pool in shared memory would do).
 // Reports useful lane-steps / (32 x warp-steps) and the warp instruction estimate of each (C_node, C_tri from the SASS).
 // Analysis tool only.  Build like tools/bvh_quality.cpp; usage: bvh_lockstep scene.txt asset_dir [W H [spp]]
 #include <algorithm>
@@ -123,7 +125,10 @@ int main(int argc, char** argv)
         int root = L.mesh_root[lf.payload];
         if (root < 0) continue;
         const double* m = lf.w2m;
-        double costA = 0, costB = 0, ideal = 0;
+        double costA = 0, costB = 0, costC = 0, ideal = 0;
+        const int POOL = 4;
+        std::vector<Lane> pool; pool.reserve(32 * POOL);
+        Sim simC{L, d};
         long warps = 0;
         std::vector<Lane> lanes(32), lanesB(32);
         Sim simA{L, d}, simB{L, d};
@@ -143,7 +148,38 @@ int main(int argc, char** argv)
                         l.bt = INFINITY; l.link = root; l.sp = 0; l.tri_i = l.tri_n = 0; l.done = false;
                     }
                 for (int q = 0; q < n; ++q) lanesB[q] = lanes[q];
+                for (int q = 0; q < n; ++q) pool.push_back(lanes[q]);
                 ++warps;
+                if (pool.size() >= (size_t)32 * POOL) {
+                    // ---- C: while-while over a pool with dynamic fetch ----
+                    size_t next = 0;
+                    std::vector<Lane> cur(32);
+                    int nl = 0;
+                    for (; nl < 32 && next < pool.size(); ++nl) cur[nl] = pool[next++];
+                    for (;;) {
+                        bool anyAlive = false;
+                        for (int q = 0; q < nl; ++q) {
+                            if (cur[q].done && next < pool.size()) cur[q] = pool[next++];  // fetch
+                            anyAlive |= !cur[q].done;
+                        }
+                        if (!anyAlive) break;
+                        for (;;) {
+                            bool any = false;
+                            for (int q = 0; q < nl; ++q) if (!cur[q].done && cur[q].link >= 0 && cur[q].link != kEmpty) { simC.nodeStep(cur[q]); any = true; }
+                            if (!any) break;
+                            costC += Cn;
+                        }
+                        int mx = 0;
+                        for (int q = 0; q < nl; ++q) if (!cur[q].done && cur[q].link < 0) { simC.enterLeaf(cur[q]); mx = std::max(mx, cur[q].tri_n); }
+                        for (int s2 = 0; s2 < mx; ++s2) {
+                            for (int q = 0; q < nl; ++q) if (!cur[q].done && cur[q].link < 0 && cur[q].tri_i < cur[q].tri_n) simC.triStep(cur[q]);
+                            costC += Ct;
+                        }
+                        for (int q = 0; q < nl; ++q) if (!cur[q].done) simC.pop(cur[q]);
+                        costC += Cp + 6;  // + the fetch bookkeeping
+                    }
+                    pool.clear();
+                }
                 long n0 = simA.nodeSteps, t0 = simA.triSteps;
                 // ---- A: while-while (the kernel) ----
                 for (;;) {
@@ -185,6 +221,7 @@ int main(int argc, char** argv)
         std::printf("  ideal (perfectly packed)      %8.1f M warp instructions\n", ideal / 1e6);
         std::printf("  A while-while (the kernel)    %8.1f M  = %.1f%% lock-step efficiency\n", costA / 1e6, 100 * ideal / costA);
         std::printf("  B if-if                       %8.1f M  = %.1f%%\n", costB / 1e6, 100 * ideal / costB);
+        std::printf("  C loop A over a pool of %d rays %8.1f M  = %.1f%% (rays still pooled at the end of the image are not counted)\n", 32 * POOL, costC / 1e6, 100 * ideal / costC);
     }
     ftbf_destroy(fs);
     return 0;

@@ -20,6 +20,10 @@ build)
   bash tools/ab_build.sh mb6    "-DFTB_MIN_BLOCKS=6"
   bash tools/ab_build.sh mb8    "-DFTB_MIN_BLOCKS=8"
   bash tools/ab_build.sh mb6cur "-DFTB_MIN_BLOCKS=6 -DFTB_CURSOR_SMEM=1"
+  # lanes idle when both blend-ring slots still wait for a long sample: with the traversal's cost variance a third / fourth
+  # unit in flight may pay on meshes although it does not elsewhere
+  bash tools/ab_build.sh rs3    "-DFTB_RING_SLOTS=3"
+  bash tools/ab_build.sh rs4    "-DFTB_RING_SLOTS=4"
   # every general CSG item of the bundled scenes is `subtract (solidCylinder) (sphere)`: with operands that may be runs of
   # leaves it becomes a register-resident pair and the house family no longer needs the general evaluator (variant 0x34b)
   AB_MAKE_ARGS="EXTRA=-DFTB_PAIR_GROUPS=1 'F32_FEATS=0x3ff 0x000 0x100 0x209 0x34b 0x3c3 0x050 0x030 0x004'" bash tools/ab_build.sh groups ""
@@ -31,7 +35,7 @@ run)
     FTB_LIB=$PWD/ab/libftb_$lib.so timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_fuzz.py tests/test_golden.py -m gpu -x -q 2>&1 | tail -n 2
   done
   bash tools/ab_bench.sh "cfg2-hollow-sphere cfg3-house cfg3-night-house cfg4-bunny-full-d14 cfg5-moon cfg5-repeat" "tree $LIBS"
-  bash tools/ab_bench.sh "cfg4-bunny cfg4-bunny-d12 cfg4-bunny-full-d14" "tree mb6 mb8 mb6cur"
+  bash tools/ab_bench.sh "cfg4-bunny cfg4-bunny-d12 cfg4-bunny-full-d14" "tree mb6 mb8 mb6cur rs3 rs4"
   for lib in groups groupscur; do
     echo "== parity with ab/libftb_$lib.so"
     FTB_LIB=$PWD/ab/libftb_$lib.so timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_fuzz.py tests/test_golden.py -m gpu -x -q 2>&1 | tail -n 2
