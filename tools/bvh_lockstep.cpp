@@ -4,6 +4,8 @@
 //   A  the kernel's loop: all lanes descend inner nodes until each has reached a leaf (or run dry), then all test their
 //      leaf's triangles, then pop ("while-while");
 //   B  one loop in which a lane does either one node step or one triangle test per iteration ("if-if");
+//   D  loop A with one postponed leaf per lane ("speculative traversal"): a lane that reaches a leaf parks it and keeps
+//      descending until it reaches a second one; the triangle phase then serves both;
 //   C  loop A fed from a pool: POOL consecutive warps' worth of rays (default 4 x 32) are traversed by one warp whose lanes
 //      fetch the next pooled ray the moment their own ends (what a per-warp ray pool in shared memory would do).
 // Reports useful lane-steps / (32 x warp-steps) and the warp instruction estimate of each (C_node, C_tri from the SASS).
@@ -125,7 +127,9 @@ int main(int argc, char** argv)
         int root = L.mesh_root[lf.payload];
         if (root < 0) continue;
         const double* m = lf.w2m;
-        double costA = 0, costB = 0, costC = 0, ideal = 0;
+        double costA = 0, costB = 0, costC = 0, costD = 0, ideal = 0;
+        std::vector<Lane> lanesD(32);
+        Sim simD{L, d};
         const int POOL = 4;
         std::vector<Lane> pool; pool.reserve(32 * POOL);
         Sim simC{L, d};
@@ -149,6 +153,51 @@ int main(int argc, char** argv)
                     }
                 for (int q = 0; q < n; ++q) lanesB[q] = lanes[q];
                 for (int q = 0; q < n; ++q) pool.push_back(lanes[q]);
+                for (int q = 0; q < n; ++q) lanesD[q] = lanes[q];
+                {   // ---- D: while-while with a postponed leaf ----
+                    std::vector<int> parked(n, kEmpty);
+                    for (;;) {
+                        bool anyAlive = false;
+                        for (int q = 0; q < n; ++q) anyAlive |= !lanesD[q].done || parked[q] != kEmpty;
+                        if (!anyAlive) break;
+                        for (;;) {  // descend; a lane holding a parked leaf that reaches another leaf stops here
+                            bool any = false;
+                            for (int q = 0; q < n; ++q) {
+                                Lane& l = lanesD[q];
+                                if (l.done) continue;
+                                if (l.link >= 0 && l.link != kEmpty) { simD.nodeStep(l); any = true; }
+                                if (l.link < 0 && parked[q] == kEmpty) { parked[q] = l.link; simD.pop(l); }       // park it, carry on
+                                else if (l.link == kEmpty) simD.pop(l);
+                            }
+                            if (!any) break;
+                            costD += Cn + 4;
+                        }
+                        // triangle phase: the parked leaf, then the one the lane stopped at (if any)
+                        for (int round = 0; round < 2; ++round) {
+                            int mx = 0;
+                            for (int q = 0; q < n; ++q) {
+                                Lane& l = lanesD[q];
+                                int leaf = round == 0 ? parked[q] : ((!l.done && l.link < 0) ? l.link : kEmpty);
+                                if (leaf == kEmpty) { l.tri_n = 0; l.tri_i = 0; continue; }
+                                int code = ~leaf; l.tri_first = code >> 3; l.tri_n = code & 7; l.tri_i = 0;
+                                mx = std::max(mx, l.tri_n);
+                            }
+                            for (int s2 = 0; s2 < mx; ++s2) {
+                                for (int q = 0; q < n; ++q) if (lanesD[q].tri_i < lanesD[q].tri_n) simD.triStep(lanesD[q]);
+                                costD += Ct;
+                            }
+                            if (round == 0) for (int q = 0; q < n; ++q) parked[q] = kEmpty;
+                            else for (int q = 0; q < n; ++q) if (!lanesD[q].done && lanesD[q].link < 0) simD.pop(lanesD[q]);
+                        }
+                        // entries popped while a closer hit was still parked may be stale: re-check the top against the new best t
+                        for (int q = 0; q < n; ++q) {
+                            Lane& l = lanesD[q];
+                            if (!l.done && l.link >= 0 && l.link != kEmpty) continue;
+                            if (!l.done && l.link == kEmpty) simD.pop(l);
+                        }
+                        costD += Cp;
+                    }
+                }
                 ++warps;
                 if (pool.size() >= (size_t)32 * POOL) {
                     // ---- C: while-while over a pool with dynamic fetch ----
@@ -221,6 +270,7 @@ int main(int argc, char** argv)
         std::printf("  ideal (perfectly packed)      %8.1f M warp instructions\n", ideal / 1e6);
         std::printf("  A while-while (the kernel)    %8.1f M  = %.1f%% lock-step efficiency\n", costA / 1e6, 100 * ideal / costA);
         std::printf("  B if-if                       %8.1f M  = %.1f%%\n", costB / 1e6, 100 * ideal / costB);
+        std::printf("  D loop A, one postponed leaf  %8.1f M  = %.1f%% (lane steps %ld nodes + %ld triangles)\n", costD / 1e6, 100 * ideal / costD, simD.nodeSteps, simD.triSteps);
         std::printf("  C loop A over a pool of %d rays %8.1f M  = %.1f%% (rays still pooled at the end of the image are not counted)\n", 32 * POOL, costC / 1e6, 100 * ideal / costC);
     }
     ftbf_destroy(fs);
