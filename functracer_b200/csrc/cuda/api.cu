@@ -647,8 +647,9 @@ int launchFrame(ftb_scene* sc, PerDevice* pd, const ftb_camera* cam, const ftb_r
                 F.s_count = std::min(UnitCap<R>::value, g.spp - s_base);
                 // run length: cheap samples amortise the dealing over up to 8 consecutive samples of a pixel, as long as
                 // every pixel still splits into >= 8 runs (the chain a lane can be stuck with stays 1/8 of a pixel)
+                static const int runMax = [] { const char* e = std::getenv("FTB_RUN_MAX"); int v = e ? std::atoi(e) : 8; return v < 1 ? 1 : (v > 8 ? 8 : v); }();  // A/B switch
                 int run = 1;
-                while (run < 8 && F.s_count % (run * 2) == 0 && F.s_count / (run * 2) >= 8) run *= 2;
+                while (run < runMax && F.s_count % (run * 2) == 0 && F.s_count / (run * 2) >= 8) run *= 2;
                 F.run = run;
                 const unsigned rpp = (unsigned)(F.s_count / run);
                 F.rpp_magic = rpp <= 1 ? 0u : (unsigned)((1ull << 32) / rpp) + 1u;

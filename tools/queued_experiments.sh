@@ -36,6 +36,8 @@ run)
   done
   bash tools/ab_bench.sh "cfg2-hollow-sphere cfg3-house cfg3-night-house cfg4-bunny-full-d14 cfg5-moon cfg5-repeat" "tree $LIBS"
   bash tools/ab_bench.sh "cfg4-bunny cfg4-bunny-d12 cfg4-bunny-full-d14" "tree mb6 mb8 mb6cur rs3 rs4"
+  # run length of the sample dealing (host side, no rebuild): 16 spp deals runs of 2 samples; single samples keep a warp on fewer pixels
+  for rm in 1 2 8; do echo "== FTB_RUN_MAX=$rm"; FTB_RUN_MAX=$rm bash tools/ab_bench.sh "cfg4-bunny-full-d14 cfg3-house cfg5-moon" "tree"; done
   for lib in groups groupscur; do
     echo "== parity with ab/libftb_$lib.so"
     FTB_LIB=$PWD/ab/libftb_$lib.so timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_fuzz.py tests/test_golden.py -m gpu -x -q 2>&1 | tail -n 2
