@@ -294,4 +294,4 @@ def test_bound_table_cannot_change_a_pixel():
     prim_diff = float((got["prim"] != got2["prim"]).mean())
     rgb_diff = float((np.abs(got["rgb"] - got2["rgb"]).max(axis=-1) > 1e-4).mean())
     print("table vs no table: prim mismatch %.2e, pixels off by > 1e-4: %.2e" % (prim_diff, rgb_diff))
-    assert prim_diff <= 5e-4 and rgb_diff <= 1e-3  # a culled occluder or shadow would be hundreds of pixels
+    assert prim_diff <= 3e-4 and rgb_diff <= 3e-4  # the smallest shadow in the picture is ~20 pixels, most are hundreds
