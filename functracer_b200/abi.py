@@ -5,7 +5,7 @@ checks sizes and that the shared library exports every declared symbol.
 """
 import ctypes as C
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # ftb_status
 OK = 0
@@ -101,7 +101,8 @@ class RenderParams(C.Structure):
                 ("jitter_xy", C.POINTER(C.c_double)), ("recursion_limit", C.c_int32),
                 ("precision", C.c_int32), ("seed", C.c_uint64), ("out_format", C.c_int32),
                 ("shard_index", C.c_int32), ("shard_count", C.c_int32), ("n_gpus", C.c_int32),
-                ("collect_stats", C.c_int32), ("reserved", C.c_int32)]
+                ("collect_stats", C.c_int32), ("band_index", C.c_int32), ("band_count", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 class DebugOut(C.Structure):
@@ -129,5 +130,6 @@ class Stats(C.Structure):
 EXPORTS = [
     "ftb_abi_version", "ftb_device_count", "ftb_last_error", "ftb_scene_create", "ftb_scene_destroy",
     "ftb_render", "ftb_tile_buffer_bytes", "ftb_render_tiles_device", "ftb_assemble_device",
-    "ftb_shade_rays",
+    "ftb_shade_rays", "ftb_band_rows", "ftb_assemble_rows_device", "ftb_host_copy_begin", "ftb_host_copy_finish",
+    "ftb_check_overflow",
 ]

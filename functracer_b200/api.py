@@ -53,6 +53,16 @@ def lib():
         L.ftb_shade_rays.argtypes = [vp, C.POINTER(C.c_double), C.c_int64, C.POINTER(abi.RenderParams),
                                      C.POINTER(C.c_double), C.POINTER(abi.DebugOut), C.POINTER(abi.Stats)]
         L.ftb_shade_rays.restype = C.c_int
+        L.ftb_band_rows.argtypes = [C.POINTER(abi.RenderParams), C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.ftb_band_rows.restype = C.c_int
+        L.ftb_assemble_rows_device.argtypes = [C.POINTER(abi.RenderParams), C.POINTER(vp), vp, C.c_int, C.c_int, vp]
+        L.ftb_assemble_rows_device.restype = C.c_int
+        L.ftb_host_copy_begin.argtypes = [vp, vp, vp, C.c_int64, vp]
+        L.ftb_host_copy_begin.restype = C.c_int
+        L.ftb_host_copy_finish.argtypes = [vp]
+        L.ftb_host_copy_finish.restype = C.c_int
+        L.ftb_check_overflow.argtypes = [vp, vp]
+        L.ftb_check_overflow.restype = C.c_int
         if L.ftb_abi_version() != abi.ABI_VERSION:
             raise RuntimeError("ABI version mismatch: library %d, bindings %d" % (L.ftb_abi_version(), abi.ABI_VERSION))
         _LIB = L
@@ -66,7 +76,7 @@ def _check(rc):
 
 def make_params(width, height, spp, jitter_xy=None, sampling=abi.SAMPLING_JITTER, recursion_limit=8, seed=1234,
                 precision=abi.PRECISION_FP32, out_format=abi.OUT_RGB_F64, shard_index=0, shard_count=1, n_gpus=0,
-                collect_stats=0):
+                collect_stats=0, band_index=0, band_count=0):
     p = abi.RenderParams()
     p.width, p.height, p.spp, p.sampling = width, height, spp, sampling
     keep = None
@@ -76,6 +86,7 @@ def make_params(width, height, spp, jitter_xy=None, sampling=abi.SAMPLING_JITTER
         p.jitter_xy = keep.ctypes.data_as(C.POINTER(C.c_double))
     p.recursion_limit, p.precision, p.seed, p.out_format = recursion_limit, precision, seed, out_format
     p.shard_index, p.shard_count, p.n_gpus, p.collect_stats = shard_index, shard_count, n_gpus, collect_stats
+    p.band_index, p.band_count = band_index, band_count
     p._keep = keep
     return p
 
@@ -165,6 +176,31 @@ class Scene:
         _check(lib().ftb_render_tiles_device(self._h, cam, C.byref(p), C.c_void_p(d_tiles_ptr), None,
                                              C.byref(st) if st is not None else None, C.c_void_p(stream)))
         return st
+
+    def check_overflow(self, stream=0):
+        """Waits for `stream`; raises FtbError(ERR_HIT_OVERFLOW) if a frame rendered through the device entry points on the
+        current device overflowed a per-ray stack since the last check."""
+        _check(lib().ftb_check_overflow(self._h, C.c_void_p(stream)))
+
+    def host_copy_begin(self, d_src_ptr, host_array, stream=0, offset=0, nbytes=None):
+        """Queues device -> host_array[offset : offset + nbytes] (bytes) behind `stream`; pageable destinations are staged
+        through the scene's page-locked ring.  Complete with host_copy_finish()."""
+        n = host_array.nbytes - offset if nbytes is None else nbytes
+        _check(lib().ftb_host_copy_begin(self._h, C.c_void_p(d_src_ptr), C.c_void_p(host_array.ctypes.data + offset), n, C.c_void_p(stream)))
+
+    def host_copy_finish(self):
+        _check(lib().ftb_host_copy_finish(self._h))
+
+
+def band_rows(p, band_index, band_count):
+    y0, y1 = C.c_int(), C.c_int()
+    _check(lib().ftb_band_rows(C.byref(p), band_index, band_count, C.byref(y0), C.byref(y1)))
+    return y0.value, y1.value
+
+
+def assemble_rows_device(p, d_tile_ptrs, d_out_ptr, y0, y1, stream=0):
+    arr = (C.c_void_p * len(d_tile_ptrs))(*[C.c_void_p(x) for x in d_tile_ptrs])
+    _check(lib().ftb_assemble_rows_device(C.byref(p), arr, C.c_void_p(d_out_ptr), y0, y1, C.c_void_p(stream)))
 
 
 def tile_buffer_bytes(p):

@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <functional>
 #include <map>
 #include <memory>
@@ -193,6 +194,79 @@ struct PerDevice;
 template <typename R> SceneStorage<R>& storageOf(PerDevice* pd);
 typedef std::function<int(int)> ChunkDone;  // called after the launches of chunk k have been queued
 
+// Device -> host copies into memory the caller did not page-lock (a GC-pinned .NET array, a std::vector, numpy):
+// cudaMemcpyAsync to pageable memory is staged by the driver and does not return before the copy is done, which would
+// serialise the banded frame download with the rendering.  Pieces of <= kSlotBytes go device -> a page-locked ring at
+// link speed and the calling thread copies finished pieces on to the destination while later ones are in flight.
+struct HostCopier {
+    static constexpr size_t kSlotBytes = 16u << 20;
+    static constexpr int kSlots = 4;
+    char* ring = nullptr;
+    cudaEvent_t ev[kSlots] = {nullptr, nullptr, nullptr, nullptr};
+    struct Piece { char* dst; size_t bytes; int slot; };
+    std::deque<Piece> pending;  // staged pieces not yet copied out, oldest first
+    std::vector<cudaStream_t> direct;  // streams that carry copies straight into page-locked destinations
+    int next = 0;
+
+    static bool pageLocked(const void* p)
+    {
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+        return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+    }
+    cudaError_t drainOne()
+    {
+        const Piece p = pending.front();
+        pending.pop_front();
+        cudaError_t e = cudaEventSynchronize(ev[p.slot]);
+        if (e != cudaSuccess) return e;
+        std::memcpy(p.dst, ring + (size_t)p.slot * kSlotBytes, p.bytes);
+        return cudaSuccess;
+    }
+    cudaError_t begin(const void* d_src, void* host_dst, size_t bytes, cudaStream_t stream)
+    {
+        if (bytes == 0) return cudaSuccess;
+        static const bool noStage = std::getenv("FTB_NO_STAGING") != nullptr;  // A/B switch: hand pageable memory to the driver
+        if (noStage || pageLocked(host_dst)) {
+            cudaError_t e = cudaMemcpyAsync(host_dst, d_src, bytes, cudaMemcpyDeviceToHost, stream);
+            if (e == cudaSuccess && std::find(direct.begin(), direct.end(), stream) == direct.end()) direct.push_back(stream);
+            return e;
+        }
+        cudaError_t e;
+        if (!ring) {
+            if ((e = cudaHostAlloc((void**)&ring, kSlotBytes * kSlots, cudaHostAllocDefault)) != cudaSuccess) { ring = nullptr; return e; }
+            for (int k = 0; k < kSlots; ++k)
+                if ((e = cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming)) != cudaSuccess) return e;
+        }
+        for (size_t off = 0; off < bytes; off += kSlotBytes) {
+            const size_t n = std::min(kSlotBytes, bytes - off);
+            if ((int)pending.size() == kSlots && (e = drainOne()) != cudaSuccess) return e;
+            const int slot = next;
+            next = (next + 1) % kSlots;
+            if ((e = cudaMemcpyAsync(ring + (size_t)slot * kSlotBytes, static_cast<const char*>(d_src) + off, n, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
+            if ((e = cudaEventRecord(ev[slot], stream)) != cudaSuccess) return e;
+            pending.push_back({static_cast<char*>(host_dst) + off, n, slot});
+        }
+        return cudaSuccess;
+    }
+    cudaError_t finish()
+    {
+        cudaError_t e;
+        while (!pending.empty())
+            if ((e = drainOne()) != cudaSuccess) { pending.clear(); return e; }
+        for (cudaStream_t st : direct)
+            if ((e = cudaStreamSynchronize(st)) != cudaSuccess) { direct.clear(); return e; }
+        direct.clear();
+        return cudaSuccess;
+    }
+    void release()
+    {
+        pending.clear(); direct.clear();
+        for (int k = 0; k < kSlots; ++k) if (ev[k]) { cudaEventDestroy(ev[k]); ev[k] = nullptr; }
+        if (ring) { cudaFreeHost(ring); ring = nullptr; }
+    }
+};
+
 struct PerDevice {
     int device = -1;
     int sm_count = 0;
@@ -202,11 +276,40 @@ struct PerDevice {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, done = nullptr;
     DevBuf control, jitter, tiles, out, dbg_prim, dbg_sub, dbg_t, rays, order;
     std::vector<int> chunk_first;          // first position in the tile order of every chunk (+ end)
-    cudaStream_t copy_stream = nullptr;    // D2H of finished bands while later bands render
+    cudaStream_t copy_stream = nullptr;    // assembly / D2H of finished bands while later bands render (highest priority)
     std::vector<cudaEvent_t> band_events;
+    HostCopier copier;
     std::vector<unsigned char> order_key;  // what the cached tile order was computed for
     bool order_valid = false;
+    bool control_ready = false;      // the control block has been zeroed once
     std::vector<DevBuf> peer_tiles;  // on the gather device: one per remote shard
+
+    PerDevice() = default;
+    PerDevice(const PerDevice&) = delete;
+    PerDevice& operator=(const PerDevice&) = delete;
+    // Releases everything the device holds, also when a create / upload failed half way (the owner switches devices).
+    ~PerDevice()
+    {
+        if (device < 0) return;
+        int cur = -1;
+        if (cudaGetDevice(&cur) != cudaSuccess) cur = -1;
+        if (cudaSetDevice(device) == cudaSuccess) {
+            if (stream) cudaStreamSynchronize(stream);
+            if (copy_stream) cudaStreamSynchronize(copy_stream);
+            f32.release(); f64.release();
+            for (DevBuf* b : {&control, &jitter, &tiles, &out, &dbg_prim, &dbg_sub, &dbg_t, &rays, &order}) b->release();
+            for (DevBuf& b : peer_tiles) b.release();
+            copier.release();
+            if (ev0) cudaEventDestroy(ev0);
+            if (ev1) cudaEventDestroy(ev1);
+            if (done) cudaEventDestroy(done);
+            for (cudaEvent_t e : band_events) cudaEventDestroy(e);
+            if (stream) cudaStreamDestroy(stream);
+            if (copy_stream) cudaStreamDestroy(copy_stream);
+        }
+        (void)cudaGetLastError();
+        if (cur >= 0) cudaSetDevice(cur);
+    }
 };
 
 template <> SceneStorage<float>& storageOf<float>(PerDevice* pd) { return pd->f32; }
@@ -254,7 +357,7 @@ int uploadScene(const ftb_scene& sc, SceneStorage<R>& st)
     DevScene<R>& v = st.view;
     std::memset(&v, 0, sizeof(v));
     int rc;
-#define UP(vec, field) if ((rc = upload(st.allocs, vec, field)) != FTB_OK) return rc;
+#define UP(vec, field) if ((rc = upload(st.allocs, vec, field)) != FTB_OK) { st.release(); return rc; }
     {
         std::vector<R4> w2m, p0; std::vector<int4> meta;
         for (const Leaf& lf : L.leaves) {
@@ -342,7 +445,7 @@ int uploadScene(const ftb_scene& sc, SceneStorage<R>& st)
         };
         for (size_t t = 0; t < nt; ++t) pushTri(tris, t, 0, 0);
         // slot ids ride in the w components as reals: exact up to 2^24 in float
-        if (sizeof(R) == 4 && (L.bvh_tri.size() >= (1u << 24) || nt >= (1u << 24))) return fail(FTB_ERR_UNSUPPORTED, "more than 16M mesh triangles");
+        if (sizeof(R) == 4 && (L.bvh_tri.size() >= (1u << 24) || nt >= (1u << 24))) { st.release(); return fail(FTB_ERR_UNSUPPORTED, "more than 16M mesh triangles"); }
         for (size_t k = 0; k < L.bvh_tri.size(); ++k) pushTri(btris, (size_t)L.bvh_tri[k], (double)L.bvh_seq[k], (double)L.bvh_tri[k]);
         UP(roots, v.mesh_root) UP(box, v.bvh_box) UP(links, v.bvh_links) UP(btris, v.bvh_tris) UP(tris, v.tris)
     }
@@ -366,12 +469,15 @@ int getDevice(ftb_scene* sc, int device, PerDevice** out)
 {
     auto it = sc->devices.find(device);
     if (it == sc->devices.end()) {
-        std::unique_ptr<PerDevice> pd(new PerDevice);
+        std::unique_ptr<PerDevice> pd(new PerDevice);  // ~PerDevice releases whatever exists if one of the calls below fails
         pd->device = device;
         CK(cudaSetDevice(device));
         CK(cudaDeviceGetAttribute(&pd->sm_count, cudaDevAttrMultiProcessorCount, device));
+        int prLow = 0, prHigh = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&prLow, &prHigh));
         CK(cudaStreamCreateWithFlags(&pd->stream, cudaStreamNonBlocking));
-        CK(cudaStreamCreateWithFlags(&pd->copy_stream, cudaStreamNonBlocking));
+        // the copy stream's kernels (assembly of a finished band) go ahead of the next band's render blocks
+        CK(cudaStreamCreateWithPriority(&pd->copy_stream, cudaStreamNonBlocking, prHigh));
         CK(cudaEventCreate(&pd->ev0));
         CK(cudaEventCreate(&pd->ev1));
         CK(cudaEventCreateWithFlags(&pd->done, cudaEventDisableTiming));
@@ -383,6 +489,7 @@ int getDevice(ftb_scene* sc, int device, PerDevice** out)
 
 struct FrameGeom {
     int gw, gh, spp, tiles_x, tiles_y, n_tiles, shard_index, shard_count, n_local_tiles;
+    int band_index, band_count;  // ftb_render_tiles_device: only the tiles of one band of tile rows (band_count <= 1: all)
     long long n_samples;
     bool corner;
 };
@@ -409,6 +516,10 @@ int frameGeom(const ftb_render_params* p, FrameGeom& g)
     if (g.shard_index < 0 || g.shard_index >= g.shard_count) return fail(FTB_ERR_BAD_ARG, "shard_index out of range");
     g.n_local_tiles = (g.n_tiles - g.shard_index + g.shard_count - 1) / g.shard_count;
     g.n_samples = (long long)g.gw * g.gh * g.spp;
+    g.band_count = p->band_count > 1 ? p->band_count : 1;
+    g.band_index = p->band_count > 1 ? p->band_index : 0;
+    if (g.band_count > 64) return fail(FTB_ERR_BAD_ARG, "band_count exceeds 64");
+    if (g.band_index < 0 || g.band_index >= g.band_count) return fail(FTB_ERR_BAD_ARG, "band_index out of range");
     return FTB_OK;
 }
 
@@ -567,17 +678,21 @@ bool computeTileOrder(const ftb_scene& sc, const ftb_camera& c, const ftb_render
 // `stream`; nothing here synchronises unless stats are requested.
 template <typename R>
 int launchFrame(ftb_scene* sc, PerDevice* pd, const ftb_camera* cam, const ftb_render_params* p, const FrameGeom& g, void* d_tiles,
-                const ftb_debug_out* d_dbg, ftb_stats* stats, cudaStream_t stream, bool timeKernel, int n_chunks, const ChunkDone* chunkDone)
+                const ftb_debug_out* d_dbg, ftb_stats* stats, cudaStream_t stream, bool timeKernel, int n_chunks, const ChunkDone* chunkDone, int only_chunk)
 {
     SceneStorage<R>& st = storageOf<R>(pd);
     if (!st.ready) { int rc = uploadScene<R>(*sc, st); if (rc != FTB_OK) return rc; }
     CK(pd->control.reserve(sizeof(Control)));
-    CK(cudaMemsetAsync(pd->control.p, 0, sizeof(Control), stream));
+    if (!pd->control_ready) { CK(cudaMemset(pd->control.p, 0, sizeof(Control))); pd->control_ready = true; }
+    // The queue counter is reset before every launch, the counters only when they are asked for; the overflow flag stays
+    // up until somebody reads it (finishStats / ftb_check_overflow), so that the banded and the device paths cannot lose it.
+    if (stats && p->collect_stats) CK(cudaMemsetAsync(static_cast<Control*>(pd->control.p)->stats, 0, sizeof(static_cast<Control*>(pd->control.p)->stats), stream));
     DevFrame<R> F;
     std::memset(&F, 0, sizeof(F));
     F.mode = 0;
     F.gw = g.gw; F.gh = g.gh; F.spp = g.spp; F.tiles_x = g.tiles_x;
-    F.tiles_x_magic = ((unsigned long long)g.n_tiles * (unsigned long long)g.tiles_x < (1ull << 32)) ? (unsigned)((1ull << 32) / (unsigned)g.tiles_x) + 1u : 0u;
+    // floor(2^32 / tiles_x) + 1 does not fit 32 bits for tiles_x == 1 (frames <= 16 sample columns wide): those divide
+    F.tiles_x_magic = (g.tiles_x > 1 && (unsigned long long)g.n_tiles * (unsigned long long)g.tiles_x < (1ull << 32)) ? (unsigned)((1ull << 32) / (unsigned)g.tiles_x) + 1u : 0u;
     F.n_local_tiles = g.n_local_tiles; F.shard_index = g.shard_index; F.shard_count = g.shard_count;
     fillCamera<R>(F, *cam, p->width, p->height);
     if (!g.corner) {
@@ -630,6 +745,7 @@ int launchFrame(ftb_scene* sc, PerDevice* pd, const ftb_camera* cam, const ftb_r
     // per resident warp, but never below one warp-round of samples per block (and big frames keep big blocks, which
     // also bounds the number of atomics on the queue counter).
     for (int chunk = 0; chunk < n_chunks; ++chunk) {
+        if (only_chunk >= 0 && chunk != only_chunk) continue;
         const int first = n_chunks > 1 ? pd->chunk_first[(size_t)chunk] : 0;
         const int ntile = n_chunks > 1 ? pd->chunk_first[(size_t)chunk + 1] - first : g.n_local_tiles;
         if (ntile > 0) {
@@ -647,13 +763,16 @@ int launchFrame(ftb_scene* sc, PerDevice* pd, const ftb_camera* cam, const ftb_r
                 F.s_count = std::min(UnitCap<R>::value, g.spp - s_base);
                 // run length: cheap samples amortise the dealing over up to 8 consecutive samples of a pixel, as long as
                 // every pixel still splits into >= 8 runs (the chain a lane can be stuck with stays 1/8 of a pixel)
-                static const int runMax = [] { const char* e = std::getenv("FTB_RUN_MAX"); int v = e ? std::atoi(e) : 8; return v < 1 ? 1 : (v > 8 ? 8 : v); }();  // A/B switch
+                // Mesh scenes deal single samples: a traversal's cost varies so much between neighbouring samples that a lane
+                // stuck with a run of them holds its warp back (measured -14 % on the full-size mesh; moon +7 % the other way).
+                static const int runEnv = [] { const char* e = std::getenv("FTB_RUN_MAX"); int v = e ? std::atoi(e) : 0; return v > 8 ? 8 : v; }();  // A/B switch
+                const int runMax = runEnv > 0 ? runEnv : (sc->L.has_mesh ? 1 : 8);
                 int run = 1;
                 while (run < runMax && F.s_count % (run * 2) == 0 && F.s_count / (run * 2) >= 8) run *= 2;
                 F.run = run;
                 const unsigned rpp = (unsigned)(F.s_count / run);
                 F.rpp_magic = rpp <= 1 ? 0u : (unsigned)((1ull << 32) / rpp) + 1u;
-                if (s_base > 0 || chunk > 0) CK(cudaMemsetAsync(&ctl->tile_counter, 0, sizeof(unsigned int), stream));
+                CK(cudaMemsetAsync(&ctl->tile_counter, 0, sizeof(unsigned int), stream));
                 CK(var->launch(st.view, F, wantStats, pd->sm_count, stream, &launches));
             }
         }
@@ -665,10 +784,11 @@ int launchFrame(ftb_scene* sc, PerDevice* pd, const ftb_camera* cam, const ftb_r
 }
 
 int launchFrameAny(ftb_scene* sc, PerDevice* pd, const ftb_camera* cam, const ftb_render_params* p, const FrameGeom& g, void* d_tiles,
-                   const ftb_debug_out* d_dbg, ftb_stats* stats, cudaStream_t stream, bool timeKernel, int n_chunks = 1, const ChunkDone* chunkDone = nullptr)
+                   const ftb_debug_out* d_dbg, ftb_stats* stats, cudaStream_t stream, bool timeKernel, int n_chunks = 1, const ChunkDone* chunkDone = nullptr,
+                   int only_chunk = -1)
 {
-    if (p->precision == FTB_PRECISION_FP64_VERIFY) return launchFrame<double>(sc, pd, cam, p, g, d_tiles, d_dbg, stats, stream, timeKernel, n_chunks, chunkDone);
-    return launchFrame<float>(sc, pd, cam, p, g, d_tiles, d_dbg, stats, stream, timeKernel, n_chunks, chunkDone);
+    if (p->precision == FTB_PRECISION_FP64_VERIFY) return launchFrame<double>(sc, pd, cam, p, g, d_tiles, d_dbg, stats, stream, timeKernel, n_chunks, chunkDone, only_chunk);
+    return launchFrame<float>(sc, pd, cam, p, g, d_tiles, d_dbg, stats, stream, timeKernel, n_chunks, chunkDone, only_chunk);
 }
 
 // Reads the control block back (synchronises the stream) and folds it into stats.
@@ -677,7 +797,10 @@ int finishStats(ftb_scene* sc, PerDevice* pd, ftb_stats* stats, cudaStream_t str
     Control h;
     CK(cudaMemcpyAsync(&h, pd->control.p, sizeof(h), cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
-    if (h.overflow) *overflow = true;
+    if (h.overflow) {
+        *overflow = true;
+        CK(cudaMemsetAsync(&static_cast<Control*>(pd->control.p)->overflow, 0, sizeof(unsigned int), stream));
+    }
     if (stats) {
         fillStats(h, *sc, stats);
         if (h.overflow) stats->hit_overflow = 1;
@@ -709,6 +832,20 @@ inline size_t outBytes(const ftb_render_params* p)
     return p->out_format == FTB_OUT_RGB_F64 ? n * 24 : (p->out_format == FTB_OUT_RGB_F32 ? n * 12 : n * 4);
 }
 
+// CUDA ordinals of the devices this library runs on (compute capability 10.x), in ordinal order: what ftb_device_count
+// counts and what ftb_render(n_gpus = N) uses, so that the two agree on a box with other GPUs in it.
+std::vector<int> b200Devices()
+{
+    std::vector<int> out;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { (void)cudaGetLastError(); return out; }
+    for (int d = 0; d < n; ++d) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) out.push_back(d);
+    }
+    return out;
+}
+
 struct DeviceRestore {
     int dev = -1;
     DeviceRestore() { if (cudaGetDevice(&dev) != cudaSuccess) dev = -1; }
@@ -721,17 +858,7 @@ extern "C" {
 
 int ftb_abi_version(void) { return FTB_ABI_VERSION; }
 
-int ftb_device_count(void)
-{
-    int n = 0;
-    if (cudaGetDeviceCount(&n) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
-    int ok = 0;
-    for (int d = 0; d < n; ++d) {
-        int major = 0;
-        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) ++ok;
-    }
-    return ok;
-}
+int ftb_device_count(void) { return (int)b200Devices().size(); }
 
 const char* ftb_last_error(void) { return g_err.c_str(); }
 
@@ -776,21 +903,7 @@ void ftb_scene_destroy(ftb_scene* sc)
 {
     if (!sc) return;
     DeviceRestore restore;
-    for (auto& kv : sc->devices) {
-        PerDevice* pd = kv.second.get();
-        cudaSetDevice(pd->device);
-        if (pd->stream) cudaStreamSynchronize(pd->stream);
-        pd->f32.release(); pd->f64.release();
-        for (DevBuf* b : {&pd->control, &pd->jitter, &pd->tiles, &pd->out, &pd->dbg_prim, &pd->dbg_sub, &pd->dbg_t, &pd->rays, &pd->order}) b->release();
-        for (DevBuf& b : pd->peer_tiles) b.release();
-        if (pd->ev0) cudaEventDestroy(pd->ev0);
-        if (pd->ev1) cudaEventDestroy(pd->ev1);
-        if (pd->done) cudaEventDestroy(pd->done);
-        if (pd->stream) cudaStreamDestroy(pd->stream);
-        if (pd->copy_stream) cudaStreamDestroy(pd->copy_stream);
-        for (cudaEvent_t e : pd->band_events) cudaEventDestroy(e);
-    }
-    delete sc;
+    delete sc;  // ~PerDevice synchronises and releases every device's buffers, streams and events
 }
 
 int64_t ftb_tile_buffer_bytes(const ftb_render_params* params)
@@ -814,7 +927,7 @@ int ftb_render_tiles_device(ftb_scene* scene, const ftb_camera* camera, const ft
     if ((rc = getDevice(scene, dev, &pd)) != FTB_OK) return rc;
     if (stats) std::memset(stats, 0, sizeof(*stats));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if ((rc = launchFrameAny(scene, pd, camera, params, g, d_tiles, d_dbg, stats, s, stats != nullptr)) != FTB_OK) return rc;
+    if ((rc = launchFrameAny(scene, pd, camera, params, g, d_tiles, d_dbg, stats, s, stats != nullptr, g.band_count, nullptr, g.band_count > 1 ? g.band_index : -1)) != FTB_OK) return rc;
     if (stats) {  // the only synchronising path of this entry point
         bool overflow = false;
         if ((rc = finishStats(scene, pd, stats, s, true, &overflow)) != FTB_OK) return rc;
@@ -834,12 +947,77 @@ int ftb_assemble_device(const ftb_render_params* params, const void* const* d_ti
     return launchAssemble(params, g, d_tile_buffers, d_out, static_cast<cudaStream_t>(stream));
 }
 
+int ftb_band_rows(const ftb_render_params* params, int band_index, int band_count, int* y0, int* y1)
+{
+    if (!params || !y0 || !y1) return fail(FTB_ERR_BAD_ARG, "null argument");
+    FrameGeom g;
+    int rc = frameGeom(params, g);
+    if (rc != FTB_OK) return rc;
+    if (band_count < 1 || band_count > 64 || band_index < 0 || band_index >= band_count) return fail(FTB_ERR_BAD_ARG, "bad band");
+    if (g.corner && band_count > 1) return fail(FTB_ERR_UNSUPPORTED, "corner sampling blends across tile rows: render it as one band");
+    *y0 = std::min(params->height, bandFirstRow(band_index, band_count, g.tiles_y) * FTB_TILE_H);
+    *y1 = std::min(params->height, bandFirstRow(band_index + 1, band_count, g.tiles_y) * FTB_TILE_H);
+    return FTB_OK;
+}
+
+int ftb_assemble_rows_device(const ftb_render_params* params, const void* const* d_tile_buffers, void* d_out, int y0, int y1, void* stream)
+{
+    if (!params || !d_tile_buffers || !d_out) return fail(FTB_ERR_BAD_ARG, "null argument");
+    FrameGeom g;
+    int rc = frameGeom(params, g);
+    if (rc != FTB_OK) return rc;
+    if (y0 < 0 || y1 > params->height || y0 > y1) return fail(FTB_ERR_BAD_ARG, "bad row range");
+    for (int i = 0; i < g.shard_count; ++i)
+        if (!d_tile_buffers[i]) return fail(FTB_ERR_BAD_ARG, "null tile buffer");
+    return launchAssemble(params, g, d_tile_buffers, d_out, static_cast<cudaStream_t>(stream), y0, y1);
+}
+
+int ftb_host_copy_begin(ftb_scene* scene, const void* d_src, void* host_dst, int64_t bytes, void* stream)
+{
+    if (!scene || bytes < 0 || (bytes > 0 && (!d_src || !host_dst))) return fail(FTB_ERR_BAD_ARG, "null argument");
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); return fail(FTB_ERR_NO_DEVICE, "no CUDA device"); }
+    PerDevice* pd = nullptr;
+    int rc = getDevice(scene, dev, &pd);
+    if (rc != FTB_OK) return rc;
+    CK(pd->copier.begin(d_src, host_dst, (size_t)bytes, static_cast<cudaStream_t>(stream)));
+    return FTB_OK;
+}
+
+int ftb_host_copy_finish(ftb_scene* scene)
+{
+    if (!scene) return fail(FTB_ERR_BAD_ARG, "null argument");
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); return fail(FTB_ERR_NO_DEVICE, "no CUDA device"); }
+    PerDevice* pd = nullptr;
+    int rc = getDevice(scene, dev, &pd);
+    if (rc != FTB_OK) return rc;
+    CK(pd->copier.finish());
+    return FTB_OK;
+}
+
+int ftb_check_overflow(ftb_scene* scene, void* stream)
+{
+    if (!scene) return fail(FTB_ERR_BAD_ARG, "null argument");
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); return fail(FTB_ERR_NO_DEVICE, "no CUDA device"); }
+    PerDevice* pd = nullptr;
+    int rc = getDevice(scene, dev, &pd);
+    if (rc != FTB_OK) return rc;
+    if (!pd->control.p) { CK(cudaStreamSynchronize(static_cast<cudaStream_t>(stream))); return FTB_OK; }  // nothing rendered yet
+    bool overflow = false;
+    if ((rc = finishStats(scene, pd, nullptr, static_cast<cudaStream_t>(stream), false, &overflow)) != FTB_OK) return rc;
+    if (overflow) return fail(FTB_ERR_HIT_OVERFLOW, "a CSG operand produced more than 32 crossings on one ray");
+    return FTB_OK;
+}
+
 int ftb_render(ftb_scene* scene, const ftb_camera* camera, const ftb_render_params* params, void* out, const ftb_debug_out* dbg, ftb_stats* stats)
 {
     const auto t0 = std::chrono::steady_clock::now();
     if (!scene || !camera || !params || !out) return fail(FTB_ERR_BAD_ARG, "null argument");
     FrameGeom full;
     ftb_render_params p = *params;
+    p.band_index = 0; p.band_count = 0;  // banding is this call's own business
     int rc = frameGeom(&p, full);
     if (rc != FTB_OK) return rc;
     int ndev = 0;
@@ -847,7 +1025,12 @@ int ftb_render(ftb_scene* scene, const ftb_camera* camera, const ftb_render_para
     if (stats) std::memset(stats, 0, sizeof(*stats));
     DeviceRestore restore;
     const int n_gpus = p.n_gpus > 1 ? p.n_gpus : 1;
-    if (n_gpus > ndev) return fail(FTB_ERR_NO_DEVICE, "n_gpus exceeds the visible devices");
+    std::vector<int> devs;
+    if (n_gpus > 1) {
+        devs = b200Devices();
+        if (n_gpus > (int)devs.size()) return fail(FTB_ERR_NO_DEVICE, "n_gpus exceeds the visible sm_100 devices (ftb_device_count)");
+        devs.resize((size_t)n_gpus);
+    } else devs.push_back(restore.dev);
     if (n_gpus > 1 && p.shard_count > 1) return fail(FTB_ERR_BAD_ARG, "n_gpus > 1 cannot be combined with an external shard");
     if (n_gpus > 1 && dbg) return fail(FTB_ERR_UNSUPPORTED, "debug planes need n_gpus <= 1");
     if (full.shard_count > 1 && n_gpus == 1) {
@@ -855,56 +1038,43 @@ int ftb_render(ftb_scene* scene, const ftb_camera* camera, const ftb_render_para
         return fail(FTB_ERR_BAD_ARG, "ftb_render renders whole frames; use ftb_render_tiles_device for one shard");
     }
     const size_t rs = realSize(p.precision);
-    // ---- one GPU, plain frame: render in bands of tile rows and copy each finished band to the host while the
-    // next one renders (the D2H of a 1080p f64 frame takes half as long as rendering it) ------------------------------
+    const size_t frameBytes = outBytes(&p);
+    const size_t rowBytes = frameBytes / (size_t)p.height;
+    // The frame is rendered in bands of tile rows, on every device; a finished band is assembled and sent to the host while
+    // the next bands render (the download of a 1080p f64 frame takes half as long as rendering it, and the CPU's own copy
+    // out of the page-locked ring as long again), so only the last, smallest band's copy is exposed.
     static const bool noBands = std::getenv("FTB_NO_BANDS") != nullptr;  // A/B switch for measurements
-    if (n_gpus == 1 && !dbg && !stats && !full.corner && !noBands && (long long)p.width * p.height >= 262144 && full.tiles_y >= 8) {
-        const int kBands = 4;
-        PerDevice* pd = nullptr;
-        if ((rc = getDevice(scene, restore.dev, &pd)) != FTB_OK) return rc;
-        CK(pd->tiles.reserve((size_t)full.n_local_tiles * FTB_TILE_PIXELS * 3 * rs));
-        CK(pd->out.reserve(outBytes(&p)));
+    const bool banded = !dbg && !stats && !full.corner && !noBands && (long long)p.width * p.height >= 262144 && full.tiles_y >= 8;
+    const int kBands = banded ? 4 : 1;
+    const int primary = devs[0];
+    // A/B switch: page-lock the caller's buffer for the duration of the call instead of staging through the ring
+    static const bool hostRegister = std::getenv("FTB_HOST_REGISTER") != nullptr;
+    bool registered = false;
+    if (hostRegister && !HostCopier::pageLocked(out)) {
+        if (cudaHostRegister(out, frameBytes, cudaHostRegisterDefault) == cudaSuccess) registered = true; else (void)cudaGetLastError();
+    }
+    struct Unregister { void* p; bool on; ~Unregister() { if (on) cudaHostUnregister(p); } } unregister = {out, registered};
+
+    struct Shard { PerDevice* pd; FrameGeom g; ftb_render_params ps; void* target; bool direct; };
+    std::vector<Shard> sh((size_t)n_gpus);
+    std::vector<const void*> bufs((size_t)n_gpus);
+    // ---- render: one shard per device, every band of every device queued before anything is waited on ----------------
+    for (int k = 0; k < n_gpus; ++k) {
+        const int dev = devs[(size_t)k];
+        CK(cudaSetDevice(dev));
+        Shard& S = sh[(size_t)k];
+        if ((rc = getDevice(scene, dev, &S.pd)) != FTB_OK) return rc;
+        PerDevice* pd = S.pd;
+        S.ps = p;
+        S.ps.shard_index = n_gpus > 1 ? k : 0; S.ps.shard_count = n_gpus;
+        if ((rc = frameGeom(&S.ps, S.g)) != FTB_OK) return rc;
+        const size_t tileBytes = (size_t)S.g.n_local_tiles * FTB_TILE_PIXELS * 3 * rs;
+        CK(pd->tiles.reserve(tileBytes));
         while ((int)pd->band_events.size() < kBands) {
             cudaEvent_t e;
             CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
             pd->band_events.push_back(e);
         }
-        const size_t rowBytes = outBytes(&p) / (size_t)p.height;
-        const void* buf0 = pd->tiles.p;
-        ChunkDone bandDone = [&](int c) -> int {
-            const int r0 = bandFirstRow(c, kBands, full.tiles_y), r1 = bandFirstRow(c + 1, kBands, full.tiles_y);
-            const int y0 = std::min(p.height, r0 * FTB_TILE_H), y1 = std::min(p.height, r1 * FTB_TILE_H);
-            if (y1 <= y0) return FTB_OK;
-            int rc2 = launchAssemble(&p, full, &buf0, pd->out.p, pd->stream, y0, y1);
-            if (rc2 != FTB_OK) return rc2;
-            CK(cudaEventRecord(pd->band_events[c], pd->stream));
-            CK(cudaStreamWaitEvent(pd->copy_stream, pd->band_events[c], 0));
-            CK(cudaMemcpyAsync(static_cast<char*>(out) + (size_t)y0 * rowBytes, static_cast<const char*>(pd->out.p) + (size_t)y0 * rowBytes,
-                               (size_t)(y1 - y0) * rowBytes, cudaMemcpyDeviceToHost, pd->copy_stream));
-            return FTB_OK;
-        };
-        if ((rc = launchFrameAny(scene, pd, camera, &p, full, pd->tiles.p, nullptr, nullptr, pd->stream, false, kBands, &bandDone)) != FTB_OK) return rc;
-        bool overflow = false;
-        if ((rc = finishStats(scene, pd, nullptr, pd->stream, false, &overflow)) != FTB_OK) return rc;
-        CK(cudaStreamSynchronize(pd->copy_stream));
-        if (overflow) return fail(FTB_ERR_HIT_OVERFLOW, "a CSG operand produced more than 32 crossings on one ray");
-        return FTB_OK;
-    }
-    std::vector<PerDevice*> pds(n_gpus);
-    std::vector<const void*> bufs(n_gpus);
-    const int primary = n_gpus > 1 ? 0 : restore.dev;
-    // ---- render: one shard per device, all queued before anything is waited on ----------------------
-    for (int k = 0; k < n_gpus; ++k) {
-        const int dev = n_gpus > 1 ? k : primary;
-        CK(cudaSetDevice(dev));
-        if ((rc = getDevice(scene, dev, &pds[k])) != FTB_OK) return rc;
-        PerDevice* pd = pds[k];
-        ftb_render_params ps = p;
-        ps.shard_index = k; ps.shard_count = n_gpus;
-        FrameGeom g;
-        if ((rc = frameGeom(&ps, g)) != FTB_OK) return rc;
-        const size_t tileBytes = (size_t)g.n_local_tiles * FTB_TILE_PIXELS * 3 * rs;
-        CK(pd->tiles.reserve(tileBytes));
         ftb_debug_out ddbg = {nullptr, nullptr, nullptr};
         if (dbg && dbg->prim_id) {
             CK(pd->dbg_prim.reserve((size_t)full.n_samples * 4));
@@ -915,58 +1085,69 @@ int ftb_render(ftb_scene* scene, const ftb_camera* camera, const ftb_render_para
         }
         // Shards of the other devices: the render kernel's fold stores finished pixels straight into a buffer on the
         // primary device over NVLink (peer access), so there is no gather step; without peer access the shard is
-        // rendered locally and copied with cudaMemcpyPeerAsync.
-        void* target = pd->tiles.p;
-        bool direct = false;
+        // rendered locally and every finished band is copied with cudaMemcpyPeerAsync.
+        S.target = pd->tiles.p;
+        S.direct = false;
         if (k > 0) {
-            PerDevice* p0 = pds[0];
-            if ((int)p0->peer_tiles.size() < n_gpus) p0->peer_tiles.resize(n_gpus);
+            PerDevice* p0 = sh[0].pd;
+            if ((int)p0->peer_tiles.size() < n_gpus) p0->peer_tiles.resize((size_t)n_gpus);
             CK(cudaSetDevice(primary));
-            CK(p0->peer_tiles[k].reserve(tileBytes));
+            CK(p0->peer_tiles[(size_t)k].reserve(tileBytes));
             CK(cudaSetDevice(dev));
             int can = 0;
             if (cudaDeviceCanAccessPeer(&can, dev, primary) == cudaSuccess && can) {
                 cudaError_t pe = cudaDeviceEnablePeerAccess(primary, 0);
-                if (pe == cudaSuccess || pe == cudaErrorPeerAccessAlreadyEnabled) direct = true;
+                if (pe == cudaSuccess || pe == cudaErrorPeerAccessAlreadyEnabled) S.direct = true;
                 (void)cudaGetLastError();
             }
             static const bool noP2P = std::getenv("FTB_NO_P2P") != nullptr;  // A/B switch
-            if (noP2P) direct = false;
-            if (direct) target = p0->peer_tiles[k].p;
-        }
-        if ((rc = launchFrameAny(scene, pd, camera, &ps, g, target, ddbg.prim_id ? &ddbg : nullptr, stats, pd->stream, stats != nullptr)) != FTB_OK) return rc;
-        bufs[k] = target;
-        if (k > 0 && !direct) {
-            PerDevice* p0 = pds[0];
-            CK(cudaMemcpyPeerAsync(p0->peer_tiles[k].p, primary, pd->tiles.p, dev, tileBytes, pd->stream));
-            bufs[k] = p0->peer_tiles[k].p;
-            if (stats) stats->kernel_launches += 1;
-        }
-        CK(cudaEventRecord(pd->done, pd->stream));
+            if (noP2P) S.direct = false;
+            if (S.direct) S.target = p0->peer_tiles[(size_t)k].p;
+            bufs[(size_t)k] = p0->peer_tiles[(size_t)k].p;
+        } else bufs[0] = pd->tiles.p;
+        ChunkDone bandDone = [&, k, dev](int c) -> int {
+            Shard& Sk = sh[(size_t)k];
+            if (k > 0 && !Sk.direct) {  // the band's tiles are a contiguous run of local tiles (tile rows grow with the local index)
+                const size_t l0 = kBands > 1 ? (size_t)Sk.pd->chunk_first[(size_t)c] : 0, l1 = kBands > 1 ? (size_t)Sk.pd->chunk_first[(size_t)c + 1] : (size_t)Sk.g.n_local_tiles;
+                const size_t off = l0 * FTB_TILE_PIXELS * 3 * rs, n = (l1 - l0) * FTB_TILE_PIXELS * 3 * rs;
+                if (n) CK(cudaMemcpyPeerAsync(static_cast<char*>(sh[0].pd->peer_tiles[(size_t)k].p) + off, primary, static_cast<const char*>(Sk.pd->tiles.p) + off, dev, n, Sk.pd->stream));
+                if (stats) stats->kernel_launches += 1;
+            }
+            CK(cudaEventRecord(Sk.pd->band_events[(size_t)c], Sk.pd->stream));
+            return FTB_OK;
+        };
+        if ((rc = launchFrameAny(scene, pd, camera, &S.ps, S.g, S.target, ddbg.prim_id ? &ddbg : nullptr, stats, pd->stream, stats != nullptr, kBands, &bandDone)) != FTB_OK) return rc;
     }
-    // ---- assemble on the primary device -----------------------------------------------------------------
+    // ---- assemble + download on the primary device, band by band, behind the rendering ------------------------------------
     CK(cudaSetDevice(primary));
-    PerDevice* p0 = pds[0];
-    for (int k = 1; k < n_gpus; ++k) CK(cudaStreamWaitEvent(p0->stream, pds[k]->done, 0));
-    CK(p0->out.reserve(outBytes(&p)));
+    PerDevice* p0 = sh[0].pd;
+    CK(p0->out.reserve(frameBytes));
     ftb_render_params pa = p;
     pa.shard_index = 0; pa.shard_count = n_gpus;
     FrameGeom ga;
     if ((rc = frameGeom(&pa, ga)) != FTB_OK) return rc;
-    if ((rc = launchAssemble(&pa, ga, bufs.data(), p0->out.p, p0->stream)) != FTB_OK) return rc;
-    if (stats) stats->kernel_launches += 1;
-    CK(cudaMemcpyAsync(out, p0->out.p, outBytes(&p), cudaMemcpyDeviceToHost, p0->stream));
+    for (int c = 0; c < kBands; ++c) {
+        const int r0 = bandFirstRow(c, kBands, full.tiles_y), r1 = bandFirstRow(c + 1, kBands, full.tiles_y);
+        const int y0 = kBands > 1 ? std::min(p.height, r0 * FTB_TILE_H) : 0, y1 = kBands > 1 ? std::min(p.height, r1 * FTB_TILE_H) : p.height;
+        for (int k = 0; k < n_gpus; ++k) CK(cudaStreamWaitEvent(p0->copy_stream, sh[(size_t)k].pd->band_events[(size_t)c], 0));
+        if (y1 <= y0) continue;
+        if ((rc = launchAssemble(&pa, ga, bufs.data(), p0->out.p, p0->copy_stream, y0, y1)) != FTB_OK) return rc;
+        if (stats) stats->kernel_launches += 1;
+        CK(p0->copier.begin(static_cast<const char*>(p0->out.p) + (size_t)y0 * rowBytes, static_cast<char*>(out) + (size_t)y0 * rowBytes, (size_t)(y1 - y0) * rowBytes, p0->copy_stream));
+    }
+    CK(p0->copier.finish());
+    CK(cudaStreamSynchronize(p0->copy_stream));
+    bool overflow = false;
+    for (int k = 0; k < n_gpus; ++k) {
+        CK(cudaSetDevice(sh[(size_t)k].pd->device));
+        if ((rc = finishStats(scene, sh[(size_t)k].pd, stats, sh[(size_t)k].pd->stream, stats != nullptr, &overflow)) != FTB_OK) return rc;
+    }
+    CK(cudaSetDevice(primary));
     if (dbg && dbg->prim_id) {
         CK(cudaMemcpyAsync(dbg->prim_id, p0->dbg_prim.p, (size_t)full.n_samples * 4, cudaMemcpyDeviceToHost, p0->stream));
         if (dbg->sub_id) CK(cudaMemcpyAsync(dbg->sub_id, p0->dbg_sub.p, (size_t)full.n_samples * 4, cudaMemcpyDeviceToHost, p0->stream));
         if (dbg->t) CK(cudaMemcpyAsync(dbg->t, p0->dbg_t.p, (size_t)full.n_samples * 8, cudaMemcpyDeviceToHost, p0->stream));
     }
-    bool overflow = false;
-    for (int k = 0; k < n_gpus; ++k) {
-        CK(cudaSetDevice(pds[k]->device));
-        if ((rc = finishStats(scene, pds[k], stats, pds[k]->stream, stats != nullptr, &overflow)) != FTB_OK) return rc;
-    }
-    CK(cudaSetDevice(primary));
     CK(cudaStreamSynchronize(p0->stream));
     if (stats) stats->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     if (overflow) return fail(FTB_ERR_HIT_OVERFLOW, "a CSG operand produced more than 32 crossings on one ray");

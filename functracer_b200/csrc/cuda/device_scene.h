@@ -43,7 +43,8 @@ enum Feature : unsigned {
     FT_CSGN = 0x80,   // any other CSG item (general post-order program, inlined)
     FT_PLANAR = 0x100,  // a top-level plane / square / circle leaf exists (FP32 self-intersection guard, render.cuh)
     FT_TABLE = 0x200,  // enough top-level items for the common-origin bound table to pay (lower.h kFeatOriginTable, render.cuh)
-    FT_ALL = 0x3ff
+    FT_PAIRG = 0x400,  // a CSG pair (FT_CSG) whose operand is a run of leaves, e.g. solidCylinder (lower.cpp, render.cuh csgPair)
+    FT_ALL = 0x7ff
 };
 
 enum StatSlot : int {

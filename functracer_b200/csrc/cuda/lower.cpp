@@ -1,10 +1,6 @@
 // lower.cpp — see lower.h.
 #include "lower.h"
 
-#ifndef FTB_PAIR_GROUPS
-#define FTB_PAIR_GROUPS 0  // experiment, see render.cuh
-#endif
-
 #include <algorithm>
 #include <array>
 #include <cmath>
@@ -305,7 +301,12 @@ struct Lowerer {
 
     // Post-order program of a subtree that sits under a CSG node.  Returns the bound of what the
     // subtree can report and the list-stack depth it needs.
-    bool emitProgram(int node, Ctx cx, int depth, Sphere& bound, bool& empty, int& lists, bool& casts)
+    // closed: every line crosses the subtree's surface an even number of times (sphere, cube, solidCylinder and their
+    // combinations).  The device culls an item whose bound lies entirely behind the ray origin; for `subtract A B`
+    // (bound = A's) and `intersect A B` (bound = one operand's) that is only right if the bounding operand is closed: an open
+    // one (cylinder, cone, square, circle, triangle) crossed once at t < 0 leaves Csg.constructedSolid's inA / inB state
+    // true for all t > 0 (Csg.fs:74-94) and the reference then reports the OTHER operand's crossings ahead of the origin.
+    bool emitProgram(int node, Ctx cx, int depth, Sphere& bound, bool& empty, int& lists, bool& casts, bool& closed)
     {
         if (!checkNode(node, depth)) return false;
         const ftb_node& n = d.nodes[node];
@@ -322,47 +323,58 @@ struct Lowerer {
             }
             if (lv.size() != 1) L.ops.push_back({OP_GROUP, (int)lv.size()});
             lists = (int)lv.size();
+            closed = n.a == FTB_PRIM_SPHERE || n.a == FTB_PRIM_CUBE || n.a == FTB_PRIM_SOLIDCYLINDER;
             return true;
         }
         case FTB_NODE_TRANSFORM:
             if (n.a < 0 || n.a >= d.n_transforms) return fail(FTB_ERR_BAD_SCENE, "bad transform index");
             { M34 t; std::memcpy(t.m, d.transforms[n.a].w2m, sizeof(t.m)); cx.w2m = mul(t, cx.w2m); }
-            return emitProgram(n.b, cx, depth + 1, bound, empty, lists, casts);
+            return emitProgram(n.b, cx, depth + 1, bound, empty, lists, casts, closed);
         case FTB_NODE_MATERIAL:
             if (n.a < 0 || n.a >= d.n_materials) return fail(FTB_ERR_BAD_SCENE, "bad material index");
             cx.ops.push_back({n.kind, n.a});
-            return emitProgram(n.b, cx, depth + 1, bound, empty, lists, casts);
+            return emitProgram(n.b, cx, depth + 1, bound, empty, lists, casts, closed);
         case FTB_NODE_TEXTURE: case FTB_NODE_HUESHIFT: case FTB_NODE_IGNORELIGHT:
             cx.ops.push_back({n.kind, n.a});
-            return emitProgram(n.b, cx, depth + 1, bound, empty, lists, casts);
+            return emitProgram(n.b, cx, depth + 1, bound, empty, lists, casts, closed);
         case FTB_NODE_GROUP: {
             if (n.b < 0 || n.a < 0 || n.a + n.b > d.n_children) return fail(FTB_ERR_BAD_SCENE, "bad group range");
-            bound = kEmpty; empty = true; lists = 0;
+            bound = kEmpty; empty = true; lists = 0; closed = true;
             if (n.b == 0) { L.ops.push_back({OP_EMPTY, 0}); lists = 1; return true; }
             for (int i = 0; i < n.b; ++i) {
-                Sphere b; bool e; int l;
-                if (!emitProgram(d.children[n.a + i], cx, depth + 1, b, e, l, casts)) return false;
+                Sphere b; bool e; int l; bool c = false;
+                if (!emitProgram(d.children[n.a + i], cx, depth + 1, b, e, l, casts, c)) return false;
                 bound = enclose(bound, b, empty, e); empty = empty && e;
                 lists = std::max(lists, i + l);
+                closed = closed && c;
             }
             if (n.b != 1) L.ops.push_back({OP_GROUP, n.b});
             return true;
         }
         case FTB_NODE_UNION: case FTB_NODE_INTERSECT: case FTB_NODE_SUBTRACT: case FTB_NODE_EXCLUDE: {
-            Sphere ba, bb; bool ea, eb; int la, lb;
-            if (!emitProgram(n.a, cx, depth + 1, ba, ea, la, casts)) return false;
-            if (!emitProgram(n.b, cx, depth + 1, bb, eb, lb, casts)) return false;
+            Sphere ba, bb; bool ea, eb; int la, lb; bool ca = false, cb = false;
+            if (!emitProgram(n.a, cx, depth + 1, ba, ea, la, casts, ca)) return false;
+            if (!emitProgram(n.b, cx, depth + 1, bb, eb, lb, casts, cb)) return false;
             lists = std::max(la, 1 + lb);
+            closed = ca && cb;
             switch (n.kind) {
             case FTB_NODE_UNION: L.ops.push_back({OP_UNION, 0}); bound = enclose(ba, bb, ea, eb); empty = ea && eb; break;
             case FTB_NODE_EXCLUDE: L.ops.push_back({OP_EXCLUDE, 0}); bound = enclose(ba, bb, ea, eb); empty = ea && eb; break;
-            case FTB_NODE_SUBTRACT: L.ops.push_back({OP_SUBTRACT, 0}); bound = ba; empty = ea; break;
-            default:  // intersect: every reported crossing lies inside both operands' bounds
+            case FTB_NODE_SUBTRACT:  // every reported crossing lies inside A's bound - as long as A is closed (see above)
+                L.ops.push_back({OP_SUBTRACT, 0});
+                bound = ca ? ba : kUnbounded; empty = ea;
+                break;
+            default:  // intersect: every reported crossing lies inside both operands' bounds; the bounding operand must be closed
                 L.ops.push_back({OP_INTERSECT, 0});
                 if (ea || eb) { bound = kEmpty; empty = true; }
-                else if (ba.r < 0) { bound = bb; empty = false; }
-                else if (bb.r < 0) { bound = ba; empty = false; }
-                else { bound = (ba.r <= bb.r) ? ba : bb; empty = false; }
+                else {
+                    const bool useA = ca && ba.r >= 0, useB = cb && bb.r >= 0;
+                    if (useA && useB) bound = (ba.r <= bb.r) ? ba : bb;
+                    else if (useA) bound = ba;
+                    else if (useB) bound = bb;
+                    else bound = kUnbounded;
+                    empty = false;
+                }
                 break;
             }
             L.has_csg = true;
@@ -414,8 +426,8 @@ struct Lowerer {
             return true;
         case FTB_NODE_UNION: case FTB_NODE_INTERSECT: case FTB_NODE_SUBTRACT: case FTB_NODE_EXCLUDE: {
             int first = (int)L.ops.size();
-            Sphere b; bool e = true; int lists = 0; bool casts = false;
-            if (!emitProgram(node, cx, depth, b, e, lists, casts)) return false;
+            Sphere b; bool e = true; int lists = 0; bool casts = false, closed = false;
+            if (!emitProgram(node, cx, depth, b, e, lists, casts, closed)) return false;
             L.max_csg_lists = std::max(L.max_csg_lists, lists);
             const int count = (int)L.ops.size() - first;
             pushItem(ITEM_CSG, first, count, casts, b, e);
@@ -425,11 +437,11 @@ struct Lowerer {
                 it.kind = ITEM_CSG2 | (L.ops[first + 2].kind << 8);
                 it.a = L.ops[first].arg; it.b = L.ops[first + 1].arg;
             }
-#if FTB_PAIR_GROUPS
             else {
-                // Experiment: an operand may also be a Group of consecutive leaves (solidCylinder = [top; bottom; sides],
+                // An operand may also be a Group of consecutive leaves (solidCylinder = [top; bottom; sides],
                 // Cylinder.fs:25-29): `LEAF l .. LEAF l+k-1, GROUP k`.  The item stays a pair, each operand a run of leaves:
-                // a / b = first leaf | (leaves - 1) << 24.  Every CSG item of the bundled scenes has this shape.
+                // a / b = first leaf | (leaves - 1) << 24 (kernel feature FT_PAIRG).  Every CSG item of the bundled scenes
+                // has one of these two shapes.
                 auto operand = [&](int& at, int& packed) -> bool {
                     if (at >= first + count || L.ops[at].kind != OP_LEAF) return false;
                     const int l0 = L.ops[at].arg;
@@ -450,7 +462,6 @@ struct Lowerer {
                     it.a = pa; it.b = pb;
                 }
             }
-#endif
             return true;
         }
         default: return fail(FTB_ERR_BAD_SCENE, "bad node kind");
@@ -647,7 +658,8 @@ int lower_scene(const ftb_scene_desc& d, Lowered& out, std::string& err)
         if (lf.kind == LEAF_TRIANGLE || lf.kind == LEAF_MESH) f |= 0x04;
     }
     for (const Item& it : out.items) {
-        if ((it.kind & 0xff) == ITEM_CSG2) f |= 0x08;  // a two-leaf CSG pair
+        if ((it.kind & 0xff) == ITEM_CSG2) f |= 0x08;  // a two-operand CSG pair
+        if ((it.kind & 0xff) == ITEM_CSG2 && ((it.a >> 24) || (it.b >> 24))) f |= 0x400;  // ... with a run of leaves as an operand
         if (it.kind == ITEM_CSG) f |= 0x80;            // a general CSG program
     }
     if (out.has_texture) f |= 0x10;

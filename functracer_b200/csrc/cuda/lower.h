@@ -41,9 +41,10 @@ enum LeafKind : int32_t {
     LEAF_MESH = 8
 };
 
-// ITEM_CSG2: a CSG node whose two operands are single leaves (`subtract cube (scale .65 sphere)`): the device
-// evaluates it in registers when neither leaf yields more than two crossings; kind = ITEM_CSG2 | (CsgOpKind << 8),
-// a / b = the two leaves.  Every CSG item also keeps its general post-order program (prog_first / prog_count).
+// ITEM_CSG2: a CSG node whose two operands are single leaves (`subtract cube (scale .65 sphere)`) or Groups of
+// consecutive leaves (`subtract (solidCylinder) (sphere)`): the device evaluates it in registers when neither operand
+// yields more than two crossings; kind = ITEM_CSG2 | (CsgOpKind << 8), a / b = first leaf | (leaves - 1) << 24.
+// Every CSG item also keeps its general post-order program (prog_first / prog_count).
 enum ItemKind : int32_t { ITEM_LEAF = 0, ITEM_CSG = 1, ITEM_CSG2 = 2 };
 
 enum CsgOpKind : int32_t {
@@ -137,7 +138,8 @@ struct Lowered {
     bool has_csg = false, has_mesh = false, has_texture = false, has_image = false;
     bool has_soft_light = false, has_rough = false, has_reflection = false;
     // Kernel features this scene needs, as device_scene.h `Feature` bits (cube 1, round 2, mesh 4, csg 8,
-    // texture 16, Oren-Nayar 32, rng 64, general CSG 128, top-level planar leaf 256); camera depth of field adds rng at render time.
+    // texture 16, Oren-Nayar 32, rng 64, general CSG 128, top-level planar leaf 256, bound table 512, pair with a run operand 1024);
+    // camera depth of field adds rng at render time.
     unsigned features = 0;
 };
 

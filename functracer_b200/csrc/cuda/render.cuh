@@ -33,23 +33,6 @@
 #include "device_scene.h"
 #include "lower.h"
 
-// Experiment switches (tools/ab_build.sh NAME "-DFTB_...=v"): none of them changes a result.
-#ifndef FTB_PAIR_NETWORK
-#define FTB_PAIR_NETWORK 0  // 1: two-leaf CSG merges its <= 4 crossings with a 6-exchange network instead of 4 insertions
-#endif
-#ifndef FTB_PAIR_GROUPS
-#define FTB_PAIR_GROUPS 0  // 1: an operand of the two-leaf CSG fast path may be a Group of consecutive leaves (solidCylinder); also lower.cpp
-#endif
-#ifndef FTB_CUBE_BRANCHFREE
-#define FTB_CUBE_BRANCHFREE 0  // 1: cube faces and their sink updates as selects instead of branches
-#endif
-#ifndef FTB_TABLE_TIGHT_SLACK
-#define FTB_TABLE_TIGHT_SLACK 0  // 1: the per-ray slack of the bound table only covers what the bounds' own inflation does not
-#endif
-#ifndef FTB_CURSOR_SMEM
-#define FTB_CURSOR_SMEM 0  // 1: the warp-uniform work cursors live in shared memory between iterations instead of ~15 registers
-#endif
-
 namespace ftb {
 
 #define FTB_DEV __device__ __forceinline__
@@ -398,19 +381,6 @@ FTB_DEV void intersectLeaf(const DevScene<R>& S, int leaf, const Ray<R>& wr, Sin
             // bottom/top: w = y, (a,b) = (x,z); left/right: w = x, (a,b) = (y,z); front/back: w = z, (a,b) = (x,y).
             // num/denom signs follow each square's own frame (DESIGN.md "cube"): bottom/top: num = k - w, denom = +wd;
             // left/right/front/back (rotated frames): num = w - k, denom = -wd.
-#if FTB_CUBE_BRANCHFREE
-            // Experiment: the six faces as straight-line code (selects instead of the two branches per face): the taken
-            // branches of this block are where the cfg2 kernel waits for instruction fetch.  Same arithmetic, same order.
-#define FTB_CUBE_FACE(face, wo, wd, ao, ad, bo, bd, k, rotated)                                   \
-            {                                                                                         \
-                const R num = (rotated) ? ((wo) - R(k)) : (R(k) - (wo));                              \
-                const R denom = (rotated) ? -(wd) : (wd);                                             \
-                const bool par = abs_(denom) < eps;                                                   \
-                const R t = par ? R(0) : num / denom;                                                 \
-                const R pa = (ao) + t * (ad), pb = (bo) + t * (bd);                                   \
-                sink.hitIf((!par || num < eps) && (pa >= R(0)) && (pa <= R(1)) && (pb >= R(0)) && (pb <= R(1)), t, face); \
-            }
-#else
 #define FTB_CUBE_FACE(face, wo, wd, ao, ad, bo, bd, k, rotated)                                   \
             {                                                                                         \
                 R num = (rotated) ? ((wo) - R(k)) : (R(k) - (wo));                                    \
@@ -423,7 +393,6 @@ FTB_DEV void intersectLeaf(const DevScene<R>& S, int leaf, const Ray<R>& wr, Sin
                     if ((pa >= R(0)) && (pa <= R(1)) && (pb >= R(0)) && (pb <= R(1))) sink.hit(t, face); \
                 }                                                                                     \
             }
-#endif
             FTB_CUBE_FACE(0, oy, r.d.y, ox, r.d.x, oz, r.d.z, 0, false)
             FTB_CUBE_FACE(1, oy, r.d.y, ox, r.d.x, oz, r.d.z, 1, false)
             FTB_CUBE_FACE(2, ox, r.d.x, oy, r.d.y, oz, r.d.z, 0, true)
@@ -499,11 +468,6 @@ struct RaySink {
     {
         if (ht >= R(0) && ht < limit) { limit = ht; leaf = cur; sub = hsub; flip = 0; }
     }
-    FTB_DEV void hitIf(bool valid, R ht, int hsub)  // the same, as selects (no branch)
-    {
-        const bool take = valid && ht >= R(0) && ht < limit;
-        limit = take ? ht : limit; leaf = take ? cur : leaf; sub = take ? hsub : sub; flip = take ? 0 : flip;
-    }
     FTB_DEV bool done() const { return any && leaf >= 0; }
 };
 // CSG operand: append to the per-ray hit stack.
@@ -525,7 +489,6 @@ struct ListSink {
         if (top < kHitCap) { stack[top].t = ht; stack[top].id = (unsigned)cur | ((unsigned)(hsub & 7) << kIdSubShift); ++top; }
         else overflow = true;
     }
-    FTB_DEV void hitIf(bool valid, R ht, int hsub) { if (valid) hit(ht, hsub); }
     FTB_DEV bool done() const { return false; }
 };
 
@@ -635,103 +598,69 @@ __device__ __noinline__ CsgAnswer<R> csgGeneral(const DevScene<R>* S, int opFirs
     return ans;
 }
 
-// <= 2 crossings of one leaf, in registers.
-template <typename R>
+// <= 2 crossings of one CSG operand, in registers.  RUNS: the operand may be a run of consecutive leaves (a Group such as
+// solidCylinder = [top; bottom; sides], Cylinder.fs:25-29), so every crossing remembers the leaf it belongs to.
+template <typename R, bool RUNS>
 struct PairSink {
     static constexpr bool kIsRay = false;
     R t0, t1;
     int s0, s1, n;
-#if FTB_PAIR_GROUPS
-    int cur, l0, l1;  // the operand is a run of leaves: which one each crossing belongs to
+    int cur, l0, l1;  // RUNS only (dead otherwise)
+    FTB_DEV void clear(int first) { n = 0; t0 = t1 = R(0); s0 = s1 = 0; cur = l0 = l1 = first; }
     FTB_DEV void hit(R ht, int hsub)
     {
-        if (n == 0) { t0 = ht; s0 = hsub; l0 = cur; } else if (n == 1) { t1 = ht; s1 = hsub; l1 = cur; }
+        if (n == 0) { t0 = ht; s0 = hsub; if (RUNS) l0 = cur; } else if (n == 1) { t1 = ht; s1 = hsub; if (RUNS) l1 = cur; }
         ++n;
     }
-    FTB_DEV void hitIf(bool valid, R ht, int hsub)
-    {
-        const bool first = valid && n == 0, second = valid && n == 1;
-        t0 = first ? ht : t0; s0 = first ? hsub : s0; l0 = first ? cur : l0;
-        t1 = second ? ht : t1; s1 = second ? hsub : s1; l1 = second ? cur : l1;
-        n += valid ? 1 : 0;
-    }
-#else
-    FTB_DEV void hit(R ht, int hsub)
-    {
-        if (n == 0) { t0 = ht; s0 = hsub; } else if (n == 1) { t1 = ht; s1 = hsub; }
-        ++n;
-    }
-    FTB_DEV void hitIf(bool valid, R ht, int hsub)  // the same, as selects (no branch)
-    {
-        const bool first = valid && n == 0, second = valid && n == 1;
-        t0 = first ? ht : t0; s0 = first ? hsub : s0;
-        t1 = second ? ht : t1; s1 = second ? hsub : s1;
-        n += valid ? 1 : 0;
-    }
-#endif
     FTB_DEV bool done() const { return false; }
 };
 
-// Csg.constructedSolid (Csg.fs:74-94) for two single-leaf operands with at most two crossings each (the common
-// case: convex leaves), entirely in registers: the same stable insertion sort over A's hits then B's, the same
-// toggling walk and rule tables as evalCsg, fused with the nearest / any selection.  Returns false (nothing
-// consumed) when a leaf reports more than two crossings; the caller then runs the general program.
+// Csg.constructedSolid (Csg.fs:74-94) for two operands with at most two crossings each (the common case: convex
+// solids), entirely in registers: the same stable sort over A's hits then B's, the same toggling walk and rule tables
+// as evalCsg, fused with the nearest / any selection.  Returns false (nothing consumed) when an operand reports more
+// than two crossings; the caller then runs the general program.
+//   leafA / leafB = first leaf | (leaves - 1) << 24 (lower.cpp).  Variants without FT_PAIRG only meet single-leaf operands
+//   and inline one copy of the leaf intersectors per operand (the two copies overlap their loads: measured 13 % faster on
+//   the hollow-sphere scene than one shared copy); variants with FT_PAIRG (the house family: `subtract (solidCylinder)
+//   (sphere)` is the only CSG item of house / night-house / repeat) walk both operands' runs through ONE copy, which
+//   keeps those scenes off the general evaluator and its local-memory hit stack (measured -6 % house, -8 % repeat).
 template <typename R, unsigned FEAT, bool STATS>
 FTB_DEV bool csgPair(const DevScene<R>& S, int leafA, int leafB, int op, const Ray<R>& wr, RaySink<R>& best, Counters<STATS>& cn)
 {
+    constexpr bool RUNS = (FEAT & FT_PAIRG) != 0;
+    PairSink<R, RUNS> a, b;
+    if constexpr (RUNS) {
+        const int firstA = leafA & 0xffffff, endA = firstA + (leafA >> 24) + 1, firstB = leafB & 0xffffff, endB = firstB + (leafB >> 24) + 1;
+        a.clear(firstA); b.clear(firstB);
+#pragma unroll 1
+        for (int side = 0; side < 2; ++side) {
+            PairSink<R, RUNS> h;
+            const int first = side ? firstB : firstA, end = side ? endB : endA;
+            h.clear(first);
+#pragma unroll 1
+            for (int l = first; l < end; ++l) { h.cur = l; intersectLeaf<R, FEAT & ~FT_MESH, STATS>(S, l, wr, h, cn); }
+            if (h.n > 2) return false;
+            if (side) b = h; else a = h;
+        }
+    } else {
+        a.clear(leafA); b.clear(leafB);
+        intersectLeaf<R, FEAT & ~FT_MESH, STATS>(S, leafA, wr, a, cn);
+        if (a.n > 2) return false;
+        intersectLeaf<R, FEAT & ~FT_MESH, STATS>(S, leafB, wr, b, cn);
+        if (b.n > 2) return false;
+    }
+    cn.add(ST_CSG_OPS);
+    // Seq.sortBy (stable) as a fixed network: the four slots (A's hits, then B's; absent ones at +inf and marked invalid)
+    // go through an odd-even transposition network of six compare-exchanges that swap neighbours only when the later one
+    // is strictly smaller, which keeps equal keys in emission order (tests/test_pair_merge_equivalence.py replays it
+    // against the insertion sort of evalCsg).  Measured -6.5 % on the hollow-sphere scene against four insertions.
+    constexpr unsigned kInvalid = 0xffffffffu;
     R mt[4];
     unsigned mid[4];
-    int mn = 0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { mt[i] = R(0); mid[i] = 0u; }
-    auto insert = [&](R t, unsigned id) {  // Seq.sortBy (stable): after every element that is not greater
-        int p = 0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) p += (i < mn && !(t < mt[i])) ? 1 : 0;
-#pragma unroll
-        for (int i = 3; i >= 1; --i) if (i > p && i <= mn) { mt[i] = mt[i - 1]; mid[i] = mid[i - 1]; }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) if (i == p) { mt[i] = t; mid[i] = id; }
-        ++mn;
-    };
-    PairSink<R> a, b;
-    a.n = 0; a.t0 = a.t1 = R(0); a.s0 = a.s1 = 0;
-    b.n = 0; b.t0 = b.t1 = R(0); b.s0 = b.s1 = 0;
-#if FTB_PAIR_GROUPS
-    // leafA / leafB = first leaf | (leaves - 1) << 24 (lower.cpp): Group semantics = the leaves' crossings in list order
-    const int firstA = leafA & 0xffffff, endA = firstA + (leafA >> 24) + 1, firstB = leafB & 0xffffff, endB = firstB + (leafB >> 24) + 1;
-    a.cur = a.l0 = a.l1 = firstA;
-    b.cur = b.l0 = b.l1 = firstB;
-    // one copy of the leaf intersectors serves both operands (the variants that need this carry every leaf kind)
-#pragma unroll 1
-    for (int side = 0; side < 2; ++side) {
-        PairSink<R> h;
-        h.n = 0; h.t0 = h.t1 = R(0); h.s0 = h.s1 = 0;
-        const int first = side ? firstB : firstA, end = side ? endB : endA;
-        h.cur = h.l0 = h.l1 = first;
-#pragma unroll 1
-        for (int l = first; l < end; ++l) { h.cur = l; intersectLeaf<R, FEAT & ~FT_MESH, STATS>(S, l, wr, h, cn); }
-        if (h.n > 2) return false;
-        if (side) b = h; else a = h;
-    }
-#define FTB_PAIR_LEAF(sink, k, single) ((unsigned)((k) ? (sink).l1 : (sink).l0))
-#else
-    intersectLeaf<R, FEAT & ~FT_MESH, STATS>(S, leafA, wr, a, cn);
-    if (a.n > 2) return false;
-    intersectLeaf<R, FEAT & ~FT_MESH, STATS>(S, leafB, wr, b, cn);
-    if (b.n > 2) return false;
-#define FTB_PAIR_LEAF(sink, k, single) ((unsigned)(single))
-#endif
-    cn.add(ST_CSG_OPS);
-#if FTB_PAIR_NETWORK
-    // Experiment: the same stable sort as a fixed network.  The four slots (A's hits, then B's, absent ones at +inf and
-    // marked invalid) go through an odd-even transposition network of six compare-exchanges that swap neighbours only
-    // when the later one is strictly smaller, which keeps equal keys in emission order like Seq.sortBy.
-    constexpr unsigned kInvalid = 0xffffffffu;
-    mt[0] = a.n > 0 ? a.t0 : inf_<R>(); mid[0] = a.n > 0 ? (FTB_PAIR_LEAF(a, 0, leafA) | ((unsigned)(a.s0 & 7) << kIdSubShift)) : kInvalid;
-    mt[1] = a.n > 1 ? a.t1 : inf_<R>(); mid[1] = a.n > 1 ? (FTB_PAIR_LEAF(a, 1, leafA) | ((unsigned)(a.s1 & 7) << kIdSubShift)) : kInvalid;
-    mt[2] = b.n > 0 ? b.t0 : inf_<R>(); mid[2] = b.n > 0 ? (FTB_PAIR_LEAF(b, 0, leafB) | ((unsigned)(b.s0 & 7) << kIdSubShift) | kIdSideB) : kInvalid;
-    mt[3] = b.n > 1 ? b.t1 : inf_<R>(); mid[3] = b.n > 1 ? (FTB_PAIR_LEAF(b, 1, leafB) | ((unsigned)(b.s1 & 7) << kIdSubShift) | kIdSideB) : kInvalid;
+    mt[0] = a.n > 0 ? a.t0 : inf_<R>(); mid[0] = a.n > 0 ? ((unsigned)(RUNS ? a.l0 : leafA) | ((unsigned)(a.s0 & 7) << kIdSubShift)) : kInvalid;
+    mt[1] = a.n > 1 ? a.t1 : inf_<R>(); mid[1] = a.n > 1 ? ((unsigned)(RUNS ? a.l1 : leafA) | ((unsigned)(a.s1 & 7) << kIdSubShift)) : kInvalid;
+    mt[2] = b.n > 0 ? b.t0 : inf_<R>(); mid[2] = b.n > 0 ? ((unsigned)(RUNS ? b.l0 : leafB) | ((unsigned)(b.s0 & 7) << kIdSubShift) | kIdSideB) : kInvalid;
+    mt[3] = b.n > 1 ? b.t1 : inf_<R>(); mid[3] = b.n > 1 ? ((unsigned)(RUNS ? b.l1 : leafB) | ((unsigned)(b.s1 & 7) << kIdSubShift) | kIdSideB) : kInvalid;
     auto cx = [&](int i, int j) {
         const bool sw = mt[j] < mt[i];
         const R ti = mt[i], tj = mt[j];
@@ -740,23 +669,11 @@ FTB_DEV bool csgPair(const DevScene<R>& S, int leafA, int leafB, int op, const R
         mid[i] = sw ? ij : ii; mid[j] = sw ? ii : ij;
     };
     cx(0, 1); cx(2, 3); cx(1, 2); cx(0, 1); cx(2, 3); cx(1, 2);
-    mn = 4;
-#else
-    if (a.n > 0) insert(a.t0, FTB_PAIR_LEAF(a, 0, leafA) | ((unsigned)(a.s0 & 7) << kIdSubShift));
-    if (a.n > 1) insert(a.t1, FTB_PAIR_LEAF(a, 1, leafA) | ((unsigned)(a.s1 & 7) << kIdSubShift));
-    if (b.n > 0) insert(b.t0, FTB_PAIR_LEAF(b, 0, leafB) | ((unsigned)(b.s0 & 7) << kIdSubShift) | kIdSideB);
-    if (b.n > 1) insert(b.t1, FTB_PAIR_LEAF(b, 1, leafB) | ((unsigned)(b.s1 & 7) << kIdSubShift) | kIdSideB);
-#endif
-#undef FTB_PAIR_LEAF
     const unsigned rules = csgRuleTable(op);
     bool inA = false, inB = false, decided = false;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-#if FTB_PAIR_NETWORK
-        if (mid[k] != 0xffffffffu && !decided) {
-#else
-        if (k < mn && !decided) {
-#endif
+        if (mid[k] != kInvalid && !decided) {
             const unsigned id = mid[k];
             const R ht = mt[k];
             const bool hitB = (id & kIdSideB) != 0;
@@ -1109,8 +1026,13 @@ FTB_DEV Ray<R> primaryRay(const DevFrame<R>& F, int px, int py, int s, unsigned 
 }
 
 // ---- the kernel ------------------------------------------------------------------------------------------------------
-#ifndef FTB_MIN_BLOCKS
-#define FTB_MIN_BLOCKS 5  // <= 102 registers: 20 warps / SM measured 3-7 % faster than 16 on cfg2 / cfg3 / cfg4
+// Resident CTAs per SM.  5 (<= 102 registers, 20 warps / SM) measured 3-7 % faster than 4 on cfg2 / cfg3 and faster than
+// 6 / 8 everywhere except on the mesh-only variant, whose traversal waits on dependent node fetches: 6 CTAs there
+// (-3 % bundled mesh, -6 % full-size mesh; 8 is slower again).  The FP64 verification build passes -DFTB_MIN_BLOCKS=1.
+#ifdef FTB_MIN_BLOCKS
+template <unsigned FEAT> struct MinBlocks { static constexpr int value = FTB_MIN_BLOCKS; };
+#else
+template <unsigned FEAT> struct MinBlocks { static constexpr int value = FEAT == (unsigned)FT_MESH ? 6 : 5; };
 #endif
 #ifndef FTB_PHASE_ALIGN
 #define FTB_PHASE_ALIGN 1
@@ -1153,7 +1075,7 @@ __device__ __noinline__ void foldUnit(const R* col, const int* hdr, R* out, int 
 }
 
 template <typename R, unsigned FEAT, bool STATS>
-__global__ void __launch_bounds__(kBlockThreads, FTB_MIN_BLOCKS) render_kernel(const __grid_constant__ DevScene<R> S, const __grid_constant__ DevFrame<R> F)
+__global__ void __launch_bounds__(kBlockThreads, MinBlocks<FEAT>::value) render_kernel(const __grid_constant__ DevScene<R> S, const __grid_constant__ DevFrame<R> F)
 {
     typedef typename V4<R>::type R4;
     constexpr int CAP = UnitCap<R>::value;
@@ -1203,28 +1125,6 @@ __global__ void __launch_bounds__(kBlockThreads, FTB_MIN_BLOCKS) render_kernel(c
         }
         __syncthreads();
     }
-#if FTB_TABLE_TIGHT_SLACK
-    // Experiment.  A line that misses the common point by g passes at most g further from any centre, and every bound is
-    // already inflated by 0.002 r + 1e-5 (api.cu uploadScene): half of that is kept for the rounding of the leaf
-    // intersectors, the other half, g_allow = 0.001 r_min + 5e-6 with r_min the smallest bounded item, is room for g.  Only
-    // the excess needs the 410x slack derived above; in the bundled scenes there is none (slack 0: a sharper cull).
-    __shared__ R table_k;  // 410 * g_allow
-    if (fastBounds) {
-        __shared__ unsigned min_w_bits;  // smallest inflated r^2 as float bits (non-negative floats order like unsigned ints)
-        if (threadIdx.x == 0) min_w_bits = 0x7f800000u;
-        __syncthreads();
-        for (int j = threadIdx.x; j < S.n_items; j += kBlockThreads) {
-            const float w = (float)ldg4<R>(S.item_bound + j).w;
-            if (w >= 0.0f) atomicMin(&min_w_bits, __float_as_uint(w));
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const R r = max_((sqrt_((R)__uint_as_float(min_w_bits)) * R(1.0 - 1e-6) - R(1e-5)) / R(1.002), R(0));  // undo the inflation, rounding down
-            table_k = R(410) * (R(0.001) * r + R(5e-6));  // +inf when no item is bounded
-        }
-        __syncthreads();
-    }
-#endif
     bool overflow = false;
 
     // warp-uniform cursors: the pixel block (or 32 rays) taken from the per-GPU queue, and the unit being dealt from it
@@ -1235,31 +1135,6 @@ __global__ void __launch_bounds__(kBlockThreads, FTB_MIN_BLOCKS) render_kernel(c
 #pragma unroll
     for (int k = 0; k < kRingSlots; ++k) { remaining[k] = 0; busy[k] = false; }
     bool exhausted = false;
-#if FTB_CURSOR_SMEM
-    // Experiment: the cursors above are warp-uniform but live in vector registers (they descend from a shuffle); parked in
-    // shared memory between the dealing of one iteration and the fold of the next they free ~15 registers across the trace.
-    // Lane 0 stores, everybody reloads after a warp barrier; the values are the same in every lane by construction.
-    __shared__ int warp_cursor[WARPS][16];
-    auto parkCursors = [&]() {
-        if (lane == 0) {
-            int* w = warp_cursor[wib];
-            w[0] = blk_slot0; w[1] = blk_x0; w[2] = blk_y0; w[3] = blk_w; w[4] = blk_npix; w[5] = blk_pos;
-            w[6] = u_slot; w[7] = u_p0; w[8] = u_pos; w[9] = u_n; w[10] = exhausted ? 1 : 0;
-#pragma unroll
-            for (int k = 0; k < kRingSlots; ++k) { w[11 + 2 * k] = remaining[k]; w[12 + 2 * k] = busy[k] ? 1 : 0; }
-        }
-        __syncwarp();
-    };
-    auto fetchCursors = [&]() {
-        const int* w = warp_cursor[wib];
-        blk_slot0 = w[0]; blk_x0 = w[1]; blk_y0 = w[2]; blk_w = w[3]; blk_npix = w[4]; blk_pos = w[5];
-        u_slot = w[6]; u_p0 = w[7]; u_pos = w[8]; u_n = w[9]; exhausted = w[10] != 0;
-#pragma unroll
-        for (int k = 0; k < kRingSlots; ++k) { remaining[k] = w[11 + 2 * k]; busy[k] = w[12 + 2 * k] != 0; }
-    };
-    static_assert(11 + 2 * kRingSlots <= 16, "warp_cursor row too small");
-    parkCursors();
-#endif
 
     // per-lane sample / path state
     // where this lane's sample is parked, in one register (the kernel is register-bound: every register saved is a spill less):
@@ -1288,9 +1163,6 @@ __global__ void __launch_bounds__(kBlockThreads, FTB_MIN_BLOCKS) render_kernel(c
     const int ppu = max(1, min(32, CAP / scount));    // pixels per unit
 
     for (;;) {
-#if FTB_CURSOR_SMEM
-        fetchCursors();
-#endif
         // ---- fold units whose last sample has landed (colours were parked when each path ended) ---------------------
         if (__any_sync(full, retire)) {
             __syncwarp();  // the parked colours of every lane are visible to the lanes that fold
@@ -1376,9 +1248,6 @@ __global__ void __launch_bounds__(kBlockThreads, FTB_MIN_BLOCKS) render_kernel(c
             u_pos += min(__popc(m), avail);
             m = __ballot_sync(full, need);
         }
-#if FTB_CURSOR_SMEM
-        parkCursors();
-#endif
         if (phase == PH_START) {  // a new sample: dealt just now, or the next one of this lane's run
             if (F.mode == 0) ray = primaryRay<R, FEAT>(F, px, py, sj, sampleIndex);
             else {
@@ -1423,11 +1292,7 @@ __global__ void __launch_bounds__(kBlockThreads, FTB_MIN_BLOCKS) render_kernel(c
         }
         const HitInfo<R> h = traceScene<R, FEAT, STATS>(S, tr, phase == PH_NEAREST ? inf_<R>() : tmax, phase == PH_SHADOW, skipLeaf,
                                                         tabled ? origin_tab + (phase == PH_NEAREST ? 0 : 1 + li) * S.n_items : nullptr,
-                                                        #if FTB_TABLE_TIGHT_SLACK
-                                                        max_(R(0), (phase == PH_NEAREST ? F.primary_slack : R(4e-4) * tmax) - table_k),
-#else
                                                         phase == PH_NEAREST ? F.primary_slack : R(4e-4) * tmax,
-#endif
                                                         overflow, cn);
 
         // ---- consume the result -----------------------------------------------------------------------------------------

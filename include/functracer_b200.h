@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define FTB_ABI_VERSION 3
+#define FTB_ABI_VERSION 4
 
 typedef enum ftb_status {
     FTB_OK = 0,
@@ -221,6 +221,8 @@ typedef struct ftb_render_params {
     int32_t shard_count; /*   t % shard_count == shard_index; 0 or 1 = whole frame            */
     int32_t n_gpus;      /* ftb_render only: in-process multi-GPU, 0/1 = current device only  */
     int32_t collect_stats; /* 1 = run the counting variant of the kernel (slower) */
+    int32_t band_index;  /* ftb_render_tiles_device only: render just the tiles of band band_index of band_count    */
+    int32_t band_count;  /*   horizontal bands of tile rows (ftb_band_rows gives a band's pixel rows); 0/1 = all    */
     int32_t reserved;
 } ftb_render_params;
 
@@ -267,7 +269,16 @@ void ftb_scene_destroy(ftb_scene* scene);
 
 /* Host-buffer entry point = the drop-in for Program.fs:54-64.  out is caller-allocated:
  * W*H pixels in params->out_format, row-major (y, then x), blended (Image.fs:112-116 /
- * 134-144) and un-clamped unless RGBA8.  dbg and stats may be NULL. */
+ * 134-144) and un-clamped unless RGBA8.  dbg and stats may be NULL.
+ *
+ * out may be ordinary pageable memory (a GC-pinned .NET array, a std::vector, a numpy array): the frame is
+ * rendered in bands of tile rows, every finished band travels device -> library-owned page-locked ring ->
+ * out while the later bands render, so only the last band's copy is exposed.  CUDA page-locked memory
+ * (cudaHostAlloc / cudaHostRegister) is detected and written directly.  FTB_OUT_RGBA8 is what Image.write
+ * keeps of a frame (Image.fs:35-44: clamp, * 255, truncate) at 1/6 of the bytes of FTB_OUT_RGB_F64.
+ *
+ * One scene holds ONE frame in flight per device: the per-device scratch (tile queue counter, jitter table,
+ * tile order) is shared by all calls on that scene; concurrent frames need separate ftb_scene objects. */
 int ftb_render(ftb_scene* scene, const ftb_camera* camera, const ftb_render_params* params,
                void* out, const ftb_debug_out* dbg, ftb_stats* stats);
 
@@ -289,6 +300,31 @@ int ftb_render_tiles_device(ftb_scene* scene, const ftb_camera* camera,
                             const ftb_debug_out* d_dbg, ftb_stats* stats, void* stream);
 int ftb_assemble_device(const ftb_render_params* params, const void* const* d_tile_buffers,
                         void* d_out, void* stream);
+
+/* Banded variants for callers that overlap the frame's download with its rendering (what ftb_render does
+ * inside one process): ftb_band_rows gives the pixel rows [*y0, *y1) of band band_index of band_count
+ * (whole tile rows; later bands are smaller so that the last, exposed copy is short);
+ * ftb_render_tiles_device with params->band_count > 1 renders only that band's tiles of the shard;
+ * ftb_assemble_rows_device assembles only rows [y0, y1) of the frame (d_out still addresses row 0). */
+int ftb_band_rows(const ftb_render_params* params, int band_index, int band_count, int* y0, int* y1);
+int ftb_assemble_rows_device(const ftb_render_params* params, const void* const* d_tile_buffers,
+                             void* d_out, int y0, int y1, void* stream);
+
+/* Device -> host copy that accepts pageable destinations at full link speed.  ftb_host_copy_begin queues
+ * the copy of `bytes` from d_src (current device) behind the work already queued on `stream` and returns
+ * without waiting for that work: page-locked destinations are written directly; pageable ones go through
+ * the scene's page-locked ring (4 x 16 MB per device), the CPU copying finished pieces out while the
+ * later ones are in flight.  Pieces that do not fit in the ring are completed inside the call (so queue all
+ * rendering first, then begin the copies in the order the data becomes ready).  ftb_host_copy_finish
+ * completes every pending copy of the scene on the current device; after it returns the data is in place. */
+int ftb_host_copy_begin(ftb_scene* scene, const void* d_src, void* host_dst, int64_t bytes, void* stream);
+int ftb_host_copy_finish(ftb_scene* scene);
+
+/* The device entry points never synchronise, so a CSG hit-stack or mesh-stack overflow inside
+ * ftb_render_tiles_device cannot be returned by that call: this one waits for `stream`, returns
+ * FTB_ERR_HIT_OVERFLOW if any frame rendered on the current device since the last check overflowed
+ * (FTB_OK otherwise) and clears the flag.  ftb_render and ftb_shade_rays check by themselves. */
+int ftb_check_overflow(ftb_scene* scene, void* stream);
 
 /* Literal Shading.shade replacement (Shading.fs:141): caller supplies n explicit rays
  * (o.xyz, d.xyz per ray, i.e. what generateRays + depthOfFieldJitter produced in F#) and

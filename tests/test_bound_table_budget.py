@@ -84,14 +84,7 @@ def _true_hit(o, d, c, r, tmin, tmax):
     return hit & (far >= tmin) & (near <= tmax)
 
 
-def _tight(slack32, r):
-    """-DFTB_TABLE_TIGHT_SLACK=1: only the part of the slack that the bound's own inflation (half of 0.002 r + 1e-5, with r
-    the smallest bounded item; here the item itself, the worst case) does not already cover."""
-    return np.maximum(F(0), slack32 - (F(410) * (F(0.001) * r.astype(F) + F(5e-6))).astype(F)).astype(F)
-
-
-@pytest.mark.parametrize("tight", [False, True])
-def test_primary_rays_never_lose_a_hit(tight):
+def test_primary_rays_never_lose_a_hit():
     rng = np.random.default_rng(7)
     cam = (_rand_dirs(rng, N) * 10.0 ** rng.uniform(-1, 3, size=(N, 1))).astype(F)  # |camera| 0.1 .. 1000
     dist = 10.0 ** rng.uniform(-2, 4, size=N)                                        # camera-to-centre 0.01 .. 10 000
@@ -111,8 +104,6 @@ def test_primary_rays_never_lose_a_hit(tight):
     w = _inflated_r2(r)
     v, s = _row(centre, cam, w, +1, rng)
     slack = (F(2e-4) * np.linalg.norm(cam.astype(np.float64), axis=1)).astype(F)
-    if tight:
-        slack = _tight(slack, r)
     cand = _candidate(v, s, _unit32(d, rng), slack)
     truth = _true_hit(o.astype(np.float64), d.astype(np.float64), centre.astype(np.float64), r * 1.001 + 5e-6, 0.0, np.inf)
     assert truth.mean() > 0.3  # the generator does produce hits
@@ -125,8 +116,7 @@ def test_primary_rays_never_lose_a_hit(tight):
     assert clear.sum() > 1000 and (~cand[clear]).mean() > 0.9, (~cand[clear]).mean()
 
 
-@pytest.mark.parametrize("tight", [False, True])
-def test_point_light_shadow_rays_never_lose_a_hit(tight):
+def test_point_light_shadow_rays_never_lose_a_hit():
     rng = np.random.default_rng(11)
     light = (_rand_dirs(rng, N) * 10.0 ** rng.uniform(-1, 3, size=(N, 1))).astype(F)
     tmax_true = 10.0 ** rng.uniform(-2, 4, size=N)                                   # fragment-to-light 0.01 .. 10 000
@@ -152,8 +142,6 @@ def test_point_light_shadow_rays_never_lose_a_hit(tight):
     w = _inflated_r2(r)
     v, s = _row(centre, light, w, -1, rng)
     slack = (F(4e-4) * tmax).astype(F)
-    if tight:
-        slack = _tight(slack, r)
     cand = _candidate(v, s, _unit32(d, rng), slack)
     truth = _true_hit(frag.astype(np.float64), d.astype(np.float64), centre.astype(np.float64), r * 1.001 + 5e-6, 0.0, tmax.astype(np.float64) * (1 + 1e-6))
     assert truth.mean() > 0.2

@@ -295,3 +295,109 @@ def test_bound_table_cannot_change_a_pixel():
     rgb_diff = float((np.abs(got["rgb"] - got2["rgb"]).max(axis=-1) > 1e-4).mean())
     print("table vs no table: prim mismatch %.2e, pixels off by > 1e-4: %.2e" % (prim_diff, rgb_diff))
     assert prim_diff <= 3e-4 and rgb_diff <= 3e-4  # the smallest shadow in the picture is ~20 pixels, most are hundreds
+
+
+@pytest.mark.parametrize("w,h,sampling", [(8, 40, abi.SAMPLING_JITTER), (16, 40, abi.SAMPLING_JITTER), (15, 40, abi.SAMPLING_CORNER), (3, 70, abi.SAMPLING_JITTER)])
+def test_frames_one_tile_wide(w, h, sampling):
+    """A sample grid of at most 16 columns has tiles_x == 1: the tile -> (row, column) split of the work queue must not use
+    the multiply-high shortcut there (floor(2^32 / 1) + 1 does not fit 32 bits): every tile row has to be rendered."""
+    text = scenes.hollow_sphere(res=(w, h), spp=1)
+    if sampling == abi.SAMPLING_CORNER:
+        text = text.replace("samples 1", "samples corner")
+    for prec in (abi.PRECISION_FP64_VERIFY, abi.PRECISION_FP32):
+        ref, got = both(text, precision=prec)
+        assert (got["prim"] != -2).all()  # every sample was traced (the debug plane is pre-filled with -2 on the host)
+        check(ref, got, prec, "thin-%dx%d" % (w, h), id_frac=5e-3, within=0.995)
+
+
+def test_open_csg_operand_behind_the_origin_is_not_culled():
+    """`subtract (cylinder) B` seen from beyond the open end: the ray's line crosses the side wall once, at t < 0, which
+    leaves Csg.constructedSolid's inA state up for all t > 0 (Csg.fs:74-94), so the reference reports B's crossings
+    (AIntoAB -> Flip) although A lies entirely behind the origin.  The item's bound must not cull that."""
+    cam = "camera pos (0.3,3,0) lookat (-1.0,7,0) up (0,0,1) fov 40 ratio 1"
+    obj = "(material diffuse (0.8,0.6,0.4) reflectance 0 shineyness 0 (subtract cylinder (translate (-1.6,7,0.7) sphere)))"
+    obj2 = "(material diffuse (0.3,0.6,0.9) reflectance 0 shineyness 0 (intersect (translate (-0.4,7,-0.7) (scale 0.8 sphere)) (scale (3,1,3) cone)))"
+    text = cam + "\nsamples 1\n\n" + obj + "\n" + obj2 + "\n\ndirectional dir (0,1,0.2) colour 1\n"
+    for prec in (abi.PRECISION_FP64_VERIFY, abi.PRECISION_FP32):
+        ref, got = both(text, width=96, height=96, spp=1, precision=prec)
+        assert (ref["prim"] == 1).sum() > 100 and (ref["prim"] == 2).sum() > 1000  # both phantom spheres are in the picture
+        check(ref, got, prec, "open-operand", id_frac=5e-3, within=0.995)
+
+
+def test_pageable_pinned_and_quantised_host_frames():
+    """ftb_render into ordinary pageable memory (what a P/Invoke caller passes) goes through the page-locked ring in
+    pieces, band by band; into CUDA page-locked memory directly.  Same bits either way, in every output format, and the
+    RGBA8 frame is Image.write's quantisation (Image.fs:36-40) of the f64 one."""
+    import torch
+    W, H, spp = 1100, 720, 1
+    sc = parse(scenes.hollow_sphere(res=(W, H), spp=spp))
+    jit = frontend.jitter_pattern(2, spp)
+    with api.Scene(sc) as scene:
+        frames = {}
+        for fmt, dt, ch in ((abi.OUT_RGB_F64, np.float64, 3), (abi.OUT_RGB_F32, np.float32, 3), (abi.OUT_RGBA8, np.uint8, 4)):
+            pageable = np.full((H, W, ch), 7, dtype=dt)
+            scene.render(W, H, spp, jit, out_format=fmt, out=pageable)
+            pinned_t = torch.empty((H, W, ch), dtype={np.float64: torch.float64, np.float32: torch.float32, np.uint8: torch.uint8}[dt]).pin_memory()
+            pinned = pinned_t.numpy()
+            pinned[...] = 9
+            scene.render(W, H, spp, jit, out_format=fmt, out=pinned)
+            assert (pageable == pinned).all()
+            frames[fmt] = pageable
+        assert (frames[abi.OUT_RGB_F32] == frames[abi.OUT_RGB_F64].astype(np.float32)).all()
+        assert (frames[abi.OUT_RGBA8][..., :3] == orc.quantise(frames[abi.OUT_RGB_F32].astype(np.float64))).all()
+        # a frame larger than the 64 MB ring (pieces are recycled while the copy is in flight)
+        W2, H2 = 2600, 1500  # 93.6 MB as f64
+        big = np.zeros((H2, W2, 3), dtype=np.float64)
+        scene.render(W2, H2, 1, jit, out_format=abi.OUT_RGB_F64, out=big)
+        big32 = np.zeros((H2, W2, 3), dtype=np.float32)
+        scene.render(W2, H2, 1, jit, out_format=abi.OUT_RGB_F32, out=big32)
+        assert (big.astype(np.float32) == big32).all() and big.any()
+
+
+def test_banded_device_entry_points_and_host_copy():
+    """What one rank of the multi-process path does: render its shard band by band (ftb_render_tiles_device with
+    band_count), assemble each finished band (ftb_assemble_rows_device) and send it to a pageable host buffer
+    (ftb_host_copy_begin / _finish).  Equals the one-shot frame, bit for bit."""
+    import torch
+    W, H, spp, bands = 640, 528, 2, 4
+    sc = parse(scenes.night_house(res=(W, H), spp=spp))
+    jit = frontend.jitter_pattern(3, spp)
+    s = torch.cuda.current_stream().cuda_stream
+    with api.Scene(sc) as scene:
+        whole = scene.render(W, H, spp, jit, out_format=abi.OUT_RGBA8)["rgb"]
+        bufs = []
+        for k in range(2):
+            pk = api.make_params(W, H, spp, jit, shard_index=k, shard_count=2, out_format=abi.OUT_RGBA8)
+            bufs.append(torch.zeros(api.tile_buffer_bytes(pk), dtype=torch.uint8, device="cuda"))
+        frame = torch.zeros((H, W, 4), dtype=torch.uint8, device="cuda")
+        host = np.zeros((H, W, 4), dtype=np.uint8)
+        rows = []
+        for c in range(bands):
+            for k in range(2):
+                pk = api.make_params(W, H, spp, jit, shard_index=k, shard_count=2, out_format=abi.OUT_RGBA8, band_index=c, band_count=bands)
+                scene.render_tiles_device(pk, bufs[k].data_ptr(), stream=s)
+            y0, y1 = api.band_rows(pk, c, bands)
+            rows.append((y0, y1))
+            api.assemble_rows_device(pk, [b.data_ptr() for b in bufs], frame.data_ptr(), y0, y1, stream=s)
+            scene.host_copy_begin(frame.data_ptr() + y0 * W * 4, host, stream=s, offset=y0 * W * 4, nbytes=(y1 - y0) * W * 4)
+        scene.host_copy_finish()
+        scene.check_overflow(stream=s)
+    assert rows[0][0] == 0 and rows[-1][1] == H and all(a[1] == b[0] for a, b in zip(rows, rows[1:]))
+    assert (host == whole).all()
+
+
+def test_overflow_on_the_device_path_is_reported_by_check_overflow():
+    import torch
+    col = lambda z0: " ".join("(translate (0,0,%g) sphere)" % (z0 + 0.1 * i) for i in range(10))
+    text = one_object_scene("(union (group %s) (group %s))" % (col(0.0), col(1.0)), "directional dir (0,-1,1) colour 1")
+    sc = parse(text)
+    s = torch.cuda.current_stream().cuda_stream
+    with api.Scene(sc) as scene:
+        scene.check_overflow(stream=s)  # nothing rendered yet
+        p = api.make_params(32, 32, 1, [0.0, 0.0], out_format=abi.OUT_RGB_F32)
+        buf = torch.zeros(api.tile_buffer_bytes(p), dtype=torch.uint8, device="cuda")
+        scene.render_tiles_device(p, buf.data_ptr(), stream=s)
+        with pytest.raises(api.FtbError) as e:
+            scene.check_overflow(stream=s)
+        assert e.value.status == abi.ERR_HIT_OVERFLOW
+        scene.check_overflow(stream=s)  # the flag was cleared by the check

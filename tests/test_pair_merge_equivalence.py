@@ -1,7 +1,8 @@
-"""The two merge strategies of the two-leaf CSG fast path (render.cuh csgPair) must visit crossings in the same order.
+"""The sorting network of the two-operand CSG fast path (render.cuh csgPair) must visit crossings in the order of the
+reference's stable sort.
 
-Default: four stable insertions ("after every element that is not greater", = F# Seq.sortBy over A's hits then B's,
-Csg.fs:74-94).  Experiment -DFTB_PAIR_NETWORK=1: the four slots (absent ones = +inf, marked invalid) through an odd-even
+Reference: four stable insertions ("after every element that is not greater", = F# Seq.sortBy over A's hits then B's,
+Csg.fs:74-94; what evalCsg does).  Kernel: the four slots (absent ones = +inf, marked invalid) through an odd-even
 transposition network whose exchanges swap neighbours only when the later key is strictly smaller.  This restates both
 in Python and compares the sequence of valid ids on random inputs with many ties, zeros, infinities and absent slots.
 (NaN keys are excluded: both builds document NaN ordering as outside the parity bar)"""
