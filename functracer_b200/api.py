@@ -170,10 +170,15 @@ class Scene:
         return dict(rgb=rgb, prim=prim, sub=sub, t=t, stats=st)
 
     # -- device-buffer entry points (one process per GPU; pointers are raw device addresses) -----
-    def render_tiles_device(self, p, d_tiles_ptr, stream=0, stats=False, camera=None):
+    def render_tiles_device(self, p, d_tiles_ptr, stream=0, stats=False, camera=None, d_dbg=None):
+        """d_dbg: optional (prim_ptr, sub_ptr, t_ptr) DEVICE addresses of per-sample debug planes (0 / None = not wanted)."""
         st = abi.Stats() if stats else None
         cam = camera if camera is not None else self.parsed.camera_ptr
-        _check(lib().ftb_render_tiles_device(self._h, cam, C.byref(p), C.c_void_p(d_tiles_ptr), None,
+        dbg = None
+        if d_dbg is not None:
+            dbg = abi.DebugOut(C.cast(C.c_void_p(d_dbg[0] or None), C.POINTER(C.c_int32)), C.cast(C.c_void_p(d_dbg[1] or None), C.POINTER(C.c_int32)),
+                               C.cast(C.c_void_p(d_dbg[2] or None), C.POINTER(C.c_double)))
+        _check(lib().ftb_render_tiles_device(self._h, cam, C.byref(p), C.c_void_p(d_tiles_ptr), C.byref(dbg) if dbg is not None else None,
                                              C.byref(st) if st is not None else None, C.c_void_p(stream)))
         return st
 

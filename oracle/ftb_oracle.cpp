@@ -960,6 +960,56 @@ int ftbo_render_window(const ftb_scene_desc* desc, const ftb_camera* cam, const 
     return FTB_OK;
 }
 
+// Several pixel windows of one frame in ONE call (one thread pool, one list of 1000-ray chunks across all windows:
+// bench.py's bounded CPU samples keep every host thread busy that way), with PACKED outputs: window w's pixels
+// follow window w-1's, row-major inside the window; out_rgb holds 3 doubles per window pixel and the dbg planes spp
+// entries per window pixel, so a few stripes of an 8K x 64 spp frame do not need full-frame (8.5 GB) planes.  Jitter
+// sampling only.  rects = n_windows x (x0, y0, x1, y1).  Ray generation, RNG keys and the blend are those of
+// ftbo_render_window, i.e. of the full frame (Image.fs:97-122).
+int ftbo_render_windows_packed(const ftb_scene_desc* desc, const ftb_camera* cam, const ftb_render_params* p, int n_windows, const int* rects,
+                               double* out_rgb, const ftb_debug_out* dbg, ftb_stats* stats, int threads)
+{
+    Scene sc;
+    if (!cam || !p || !out_rgb || !rects || n_windows < 0) return fail(FTB_ERR_BAD_ARG, "null argument");
+    if (!prepare(desc, sc)) return fail(FTB_ERR_BAD_SCENE, "malformed scene graph");
+    const int W = p->width, H = p->height, spp = p->spp;
+    if (W < 1 || H < 1) return fail(FTB_ERR_BAD_ARG, "bad resolution");
+    if (p->sampling != FTB_SAMPLING_JITTER || spp < 1 || !p->jitter_xy) return fail(FTB_ERR_BAD_ARG, "packed windows need jitter sampling");
+    ImagePlane ip = createImagePlane(*cam, W, H);
+    std::vector<int64_t> first((size_t)n_windows + 1, 0);  // first packed pixel of every window
+    std::vector<int> r(rects, rects + 4 * (size_t)n_windows);
+    for (int w = 0; w < n_windows; ++w) {
+        int& x0 = r[4 * w]; int& y0 = r[4 * w + 1]; int& x1 = r[4 * w + 2]; int& y1 = r[4 * w + 3];
+        x0 = std::max(0, x0); y0 = std::max(0, y0); x1 = std::min(W, x1); y1 = std::min(H, y1);
+        if (x1 < x0) x1 = x0;
+        if (y1 < y0) y1 = y0;
+        first[(size_t)w + 1] = first[(size_t)w] + (int64_t)(x1 - x0) * (y1 - y0);
+    }
+    const int64_t npix = first[(size_t)n_windows], n = npix * spp;
+    Counters total;
+    std::vector<double> cols(3 * (size_t)n);
+    auto item = [&](int64_t i) {
+        const int s = (int)(i % spp);
+        const int64_t pix = i / spp;
+        const int w = (int)(std::upper_bound(first.begin(), first.end(), pix) - first.begin()) - 1;
+        const int x0 = r[4 * w], y0 = r[4 * w + 1], ww = r[4 * w + 2] - x0;
+        const int64_t lp = pix - first[(size_t)w];
+        const int x = x0 + (int)(lp % ww), y = y0 + (int)(lp / ww);
+        const int64_t g = ((int64_t)y * W + x) * spp + s;  // index in the reference's ray list (:104-110): the RNG key
+        Ray ray = rayThroughPixel(ip, x, y, p->jitter_xy[2 * s], p->jitter_xy[2 * s + 1]);
+        if (cam->has_focus) ray = depthOfFieldJitter(*cam, ray, p->seed, (uint64_t)g);
+        return Item{ray, (uint64_t)g, i};
+    };
+    shadeAll(sc, p, n, item, cols.data(), dbg, total, threads);
+    for (int64_t pix = 0; pix < npix; ++pix) {  // Array.average (Image.fs:112-116)
+        Col sum = {0, 0, 0};
+        for (int k = 0; k < spp; ++k) sum = cadd(sum, Col{cols[3 * (pix * spp + k)], cols[3 * (pix * spp + k) + 1], cols[3 * (pix * spp + k) + 2]});
+        out_rgb[3 * pix] = sum.r / (double)spp; out_rgb[3 * pix + 1] = sum.g / (double)spp; out_rgb[3 * pix + 2] = sum.b / (double)spp;
+    }
+    exportCounters(total, stats);
+    return FTB_OK;
+}
+
 int ftbo_render(const ftb_scene_desc* desc, const ftb_camera* cam, const ftb_render_params* p, double* out_rgb,
                 const ftb_debug_out* dbg, ftb_stats* stats, int threads)
 {

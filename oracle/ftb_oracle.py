@@ -65,6 +65,9 @@ def lib():
         L.ftbo_rough_diffuse.restype = None
         L.ftbo_primary_ray.argtypes = [C.POINTER(abi.Camera), C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, dp]
         L.ftbo_primary_ray.restype = None
+        L.ftbo_render_windows_packed.argtypes = [C.POINTER(abi.SceneDesc), C.POINTER(abi.Camera), C.POINTER(abi.RenderParams), C.c_int, C.POINTER(C.c_int),
+                                                 dp, C.POINTER(abi.DebugOut), C.POINTER(abi.Stats), C.c_int]
+        L.ftbo_render_windows_packed.restype = C.c_int
         _LIB = L
     return _LIB
 
@@ -113,6 +116,39 @@ def render(scene, params, window=None, threads=0, debug=True):
     if rc != 0:
         raise RuntimeError("oracle: %s" % L.ftbo_last_error().decode())
     return dict(rgb=rgb, prim=prim, sub=sub, t=t, stats=st)
+
+
+def render_windows(scene, params, windows, threads=0, debug=True):
+    """Several pixel windows [(x0, y0, x1, y1), ...] of one frame in one call, outputs PACKED per window.  Returns
+    dict(windows=[dict(rect, rgb[h,w,3], prim[h,w,spp], sub[h,w,spp])...], stats, seconds)."""
+    import time
+    L = lib()
+    W, H, spp = params.width, params.height, params.spp
+    rects = np.ascontiguousarray([[max(0, x0), max(0, y0), min(W, x1), min(H, y1)] for x0, y0, x1, y1 in windows], dtype=np.int32).reshape(-1, 4)
+    npix = int(((rects[:, 2] - rects[:, 0]).clip(0) * (rects[:, 3] - rects[:, 1]).clip(0)).sum())
+    rgb = np.zeros((npix, 3), dtype=np.float64)
+    prim = sub = dbg = None
+    if debug:
+        prim = np.full(npix * spp, -2, dtype=np.int32)
+        sub = np.zeros(npix * spp, dtype=np.int32)
+        dbg = abi.DebugOut(prim.ctypes.data_as(C.POINTER(C.c_int32)), sub.ctypes.data_as(C.POINTER(C.c_int32)), None)
+    st = abi.Stats()
+    t0 = time.perf_counter()
+    rc = L.ftbo_render_windows_packed(scene.desc_ptr, scene.camera_ptr, C.byref(params), len(rects), rects.ctypes.data_as(C.POINTER(C.c_int)), _dp(rgb),
+                                      C.byref(dbg) if dbg else None, C.byref(st), threads)
+    secs = time.perf_counter() - t0
+    if rc != 0:
+        raise RuntimeError("oracle: %s" % L.ftbo_last_error().decode())
+    out, at = [], 0
+    for x0, y0, x1, y1 in rects.tolist():
+        w, h = max(0, x1 - x0), max(0, y1 - y0)
+        d = dict(rect=(x0, y0, x1, y1), rgb=rgb[at:at + w * h].reshape(h, w, 3))
+        if debug:
+            d["prim"] = prim[at * spp:(at + w * h) * spp].reshape(h, w, spp)
+            d["sub"] = sub[at * spp:(at + w * h) * spp].reshape(h, w, spp)
+        out.append(d)
+        at += w * h
+    return dict(windows=out, stats=st, seconds=secs)
 
 
 def shade_rays(scene, rays_od, params, threads=0):

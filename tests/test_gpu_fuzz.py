@@ -101,7 +101,14 @@ def _scene(seed):
         else:
             lights.append("softdirectional dir (%s,%s,%s) samples %d scatter %s colour %s" % (_num(rng.uniform(-1, 1)), _num(rng.uniform(-1.5, -0.3)), _num(rng.uniform(-1, 1)),
                                                                                            int(rng.integers(1, 4)), _num(rng.uniform(2, 30)), _colour(rng)))
-    return cam + "\n" + samples + "\nres 56 40\n\n" + "\n\n".join(objs) + "\n\n" + "\n".join(lights) + "\n"
+    return cam + "\n" + samples + "\nres 128 96\n\n" + "\n\n".join(objs) + "\n\n" + "\n".join(lights) + "\n"
+
+
+# Seeds whose frames miss the default bars (FP32: colour within 1/255 on >= 99.9 % of the 128x96 pixels and <= 0.5 % primary
+# id mismatches; FP64-verify: colour within 1e-6 on >= 99.9 %, <= 0.1 % id mismatches), each with the reason found by looking
+# at the frame (tools/fuzz_debug.py SEED) and the bar it does meet: seed -> (ok64, mism64, ok32, mism32, why).
+KNOWN = {
+}
 
 
 @pytest.mark.parametrize("seed", range(160))
@@ -130,5 +137,6 @@ def test_random_scene(seed):
     ok32 = float(((d32 <= 1.0 / 255.0) | ~finite).mean())
     mism32 = float((g32["prim"] != ref["prim"]).mean())
     print("seed %d: fp64 id-mismatch %.2e colour-ok %.4f | fp32 id-mismatch %.2e colour-ok %.4f | leaves %d" % (seed, mism64, ok64, mism32, ok32, sc.desc.n_nodes))
-    assert mism64 <= 2e-3 and ok64 >= 0.997, text
-    assert mism32 <= 1e-2 and ok32 >= 0.99, text
+    b_ok64, b_m64, b_ok32, b_m32 = KNOWN.get(seed, (0.999, 1e-3, 0.999, 5e-3, ""))[:4]
+    assert mism64 <= b_m64 and ok64 >= b_ok64, text
+    assert mism32 <= b_m32 and ok32 >= b_ok32, text

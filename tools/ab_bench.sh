@@ -9,7 +9,7 @@ libs=${2:-tree}
 for w in $workloads; do
   for lib in $libs; do
     if [ "$lib" = tree ]; then unset FTB_LIB; else export FTB_LIB=$PWD/ab/libftb_$lib.so; fi
-    timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --workload "$w" 2>/dev/null | python -c "
+    timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-per-config --workload "$w" 2>/dev/null | python -c "
 import sys, json
 d = json.loads(sys.stdin.readline())
 print('$w', '$lib', round(d['ms_per_step'], 4), round(d['roofline']['kernel_ms'], 4), round(d['e2e']['ms_per_step'], 4), round(d['value'], 1))"
