@@ -273,7 +273,7 @@ def gpu_parity(run, res, windows, margin):
     m = parity.merge(parts)
     del prim, frame, tiles
     return {"frac_within_1_255": m["frac_within_1_255"], "max_err": m["max_err"], "pixels": m["pixels"], "primary_samples": m["samples"],
-            "prim_id_mismatches": m["prim_mismatch"], "prim_id_unexplained": m["prim_unexplained"], "nonfinite_pixels": m["nonfinite"],
+            "prim_id_mismatches": m["prim_mismatch"], "prim_id_unexplained": m["prim_unexplained"], "prim_id_edge_leaks": m.get("prim_edge_leak", 0), "nonfinite_pixels": m["nonfinite"],
             "note": "FP32 kernel vs the f64 CPU oracle on the cpu_baseline sample; a prim-id mismatch is explained when the oracle's own id map shows the "
                     "kernel's answer within one pixel of the sample (silhouette / tie)"}
 

@@ -194,77 +194,34 @@ struct PerDevice;
 template <typename R> SceneStorage<R>& storageOf(PerDevice* pd);
 typedef std::function<int(int)> ChunkDone;  // called after the launches of chunk k have been queued
 
-// Device -> host copies into memory the caller did not page-lock (a GC-pinned .NET array, a std::vector, numpy):
-// cudaMemcpyAsync to pageable memory is staged by the driver and does not return before the copy is done, which would
-// serialise the banded frame download with the rendering.  Pieces of <= kSlotBytes go device -> a page-locked ring at
-// link speed and the calling thread copies finished pieces on to the destination while later ones are in flight.
+// Device -> host copies of finished bands.  The destination is whatever the caller owns: usually ordinary pageable memory
+// (a GC-pinned .NET array, a std::vector, numpy), sometimes CUDA page-locked memory.  A cudaMemcpyAsync into pageable
+// memory does not return before the data is there (the driver stages it through its own page-locked buffers at link
+// speed), so the order of work is what matters: every band's render + assembly is queued FIRST, then the bands are
+// copied in the order they finish; while the host sits in the copy of band c the GPU is rendering band c + 1.
+// Measured (B200, 16 host cores, RGBA8 frame of the 8K moon scene, 132 MB): driver-staged copy +1.3 ms per frame over the
+// device-resident time, a library-owned page-locked ring + memcpy on the calling thread +5.7 ms, cudaHostRegister of
+// the caller's buffer per call +21 ms; the 1080p hollow-sphere frame: 1.43 / 1.50 / 14.6 ms.  So the driver's path it is.
 struct HostCopier {
-    static constexpr size_t kSlotBytes = 16u << 20;
-    static constexpr int kSlots = 4;
-    char* ring = nullptr;
-    cudaEvent_t ev[kSlots] = {nullptr, nullptr, nullptr, nullptr};
-    struct Piece { char* dst; size_t bytes; int slot; };
-    std::deque<Piece> pending;  // staged pieces not yet copied out, oldest first
-    std::vector<cudaStream_t> direct;  // streams that carry copies straight into page-locked destinations
-    int next = 0;
-
-    static bool pageLocked(const void* p)
-    {
-        cudaPointerAttributes a;
-        if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { (void)cudaGetLastError(); return false; }
-        return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
-    }
-    cudaError_t drainOne()
-    {
-        const Piece p = pending.front();
-        pending.pop_front();
-        cudaError_t e = cudaEventSynchronize(ev[p.slot]);
-        if (e != cudaSuccess) return e;
-        std::memcpy(p.dst, ring + (size_t)p.slot * kSlotBytes, p.bytes);
-        return cudaSuccess;
-    }
+    std::vector<cudaStream_t> used;  // streams that carry copies this frame (synchronised by finish)
     cudaError_t begin(const void* d_src, void* host_dst, size_t bytes, cudaStream_t stream)
     {
         if (bytes == 0) return cudaSuccess;
-        static const bool noStage = std::getenv("FTB_NO_STAGING") != nullptr;  // A/B switch: hand pageable memory to the driver
-        if (noStage || pageLocked(host_dst)) {
-            cudaError_t e = cudaMemcpyAsync(host_dst, d_src, bytes, cudaMemcpyDeviceToHost, stream);
-            if (e == cudaSuccess && std::find(direct.begin(), direct.end(), stream) == direct.end()) direct.push_back(stream);
-            return e;
-        }
-        cudaError_t e;
-        if (!ring) {
-            if ((e = cudaHostAlloc((void**)&ring, kSlotBytes * kSlots, cudaHostAllocDefault)) != cudaSuccess) { ring = nullptr; return e; }
-            for (int k = 0; k < kSlots; ++k)
-                if ((e = cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming)) != cudaSuccess) return e;
-        }
-        for (size_t off = 0; off < bytes; off += kSlotBytes) {
-            const size_t n = std::min(kSlotBytes, bytes - off);
-            if ((int)pending.size() == kSlots && (e = drainOne()) != cudaSuccess) return e;
-            const int slot = next;
-            next = (next + 1) % kSlots;
-            if ((e = cudaMemcpyAsync(ring + (size_t)slot * kSlotBytes, static_cast<const char*>(d_src) + off, n, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
-            if ((e = cudaEventRecord(ev[slot], stream)) != cudaSuccess) return e;
-            pending.push_back({static_cast<char*>(host_dst) + off, n, slot});
-        }
-        return cudaSuccess;
+        cudaError_t e = cudaMemcpyAsync(host_dst, d_src, bytes, cudaMemcpyDeviceToHost, stream);
+        if (e == cudaSuccess && std::find(used.begin(), used.end(), stream) == used.end()) used.push_back(stream);
+        return e;
     }
     cudaError_t finish()
     {
-        cudaError_t e;
-        while (!pending.empty())
-            if ((e = drainOne()) != cudaSuccess) { pending.clear(); return e; }
-        for (cudaStream_t st : direct)
-            if ((e = cudaStreamSynchronize(st)) != cudaSuccess) { direct.clear(); return e; }
-        direct.clear();
-        return cudaSuccess;
+        cudaError_t e = cudaSuccess;
+        for (cudaStream_t st : used) {
+            cudaError_t e2 = cudaStreamSynchronize(st);
+            if (e == cudaSuccess) e = e2;
+        }
+        used.clear();
+        return e;
     }
-    void release()
-    {
-        pending.clear(); direct.clear();
-        for (int k = 0; k < kSlots; ++k) if (ev[k]) { cudaEventDestroy(ev[k]); ev[k] = nullptr; }
-        if (ring) { cudaFreeHost(ring); ring = nullptr; }
-    }
+    void release() { used.clear(); }
 };
 
 struct PerDevice {
@@ -335,6 +292,16 @@ namespace {
 template <typename R> struct Mk4;
 template <> struct Mk4<float> { static float4 make(double a, double b, double c, double d) { return make_float4((float)a, (float)b, (float)c, (float)d); } };
 template <> struct Mk4<double> { static double4 make(double a, double b, double c, double d) { return make_double4(a, b, c, d); } };
+
+// the four child links of a BVH node as one row: int bits in FP32 (a link does not fit a float's 24 bits), exact reals in FP64
+template <typename R> typename V4<R>::type linkRow(const int32_t* c);
+template <> float4 linkRow<float>(const int32_t* c)
+{
+    float4 r;
+    std::memcpy(&r.x, &c[0], 4); std::memcpy(&r.y, &c[1], 4); std::memcpy(&r.z, &c[2], 4); std::memcpy(&r.w, &c[3], 4);
+    return r;
+}
+template <> double4 linkRow<double>(const int32_t* c) { return make_double4((double)c[0], (double)c[1], (double)c[2], (double)c[3]); }
 
 template <typename T>
 int upload(std::vector<void*>& allocs, const std::vector<T>& host, const T*& dev)
@@ -423,31 +390,40 @@ int uploadScene(const ftb_scene& sc, SceneStorage<R>& st)
         UP(texels, v.texels) UP(ii, v.img_i)
     }
     {
-        std::vector<int> roots(L.mesh_root.begin(), L.mesh_root.end()); std::vector<int2> links; std::vector<R4> box, btris, tris;
-        for (const BvhNode& n : L.bvh_nodes) {
-            if (sizeof(R) == 4) {
-                box.push_back(Mk4<R>::make(n.lo[0][0], n.lo[0][1], n.lo[0][2], n.hi[0][0]));
-                box.push_back(Mk4<R>::make(n.hi[0][1], n.hi[0][2], n.lo[1][0], n.lo[1][1]));
-                box.push_back(Mk4<R>::make(n.lo[1][2], n.hi[1][0], n.hi[1][1], n.hi[1][2]));
-            } else {
-                box.push_back(Mk4<R>::make(n.dlo[0][0], n.dlo[0][1], n.dlo[0][2], n.dhi[0][0]));
-                box.push_back(Mk4<R>::make(n.dhi[0][1], n.dhi[0][2], n.dlo[1][0], n.dlo[1][1]));
-                box.push_back(Mk4<R>::make(n.dlo[1][2], n.dhi[1][0], n.dhi[1][1], n.dhi[1][2]));
-            }
-            links.push_back(make_int2(n.child[0], n.child[1]));
+        std::vector<int> roots(L.mesh_root.begin(), L.mesh_root.end()); std::vector<R4> nodes, leaves, tris;
+        nodes.reserve(L.bvh_nodes.size() * kBvhNodeRows);
+        for (const Bvh4Node& n : L.bvh_nodes) {
+            for (int a = 0; a < 3; ++a) nodes.push_back(sizeof(R) == 4 ? Mk4<R>::make(n.lo[a][0], n.lo[a][1], n.lo[a][2], n.lo[a][3]) : Mk4<R>::make(n.dlo[a][0], n.dlo[a][1], n.dlo[a][2], n.dlo[a][3]));
+            for (int a = 0; a < 3; ++a) nodes.push_back(sizeof(R) == 4 ? Mk4<R>::make(n.hi[a][0], n.hi[a][1], n.hi[a][2], n.hi[a][3]) : Mk4<R>::make(n.dhi[a][0], n.dhi[a][1], n.dhi[a][2], n.dhi[a][3]));
+            nodes.push_back(linkRow<R>(n.child));
+            nodes.push_back(Mk4<R>::make(0, 0, 0, 0));
         }
         const size_t nt = sc.triangles.size() / 9;
-        auto pushTri = [&](std::vector<R4>& dst, size_t t, double w0, double w1) {  // v0, e1 = v1 - v0, e2 = v2 - v0 (Triangle.fs:45-46), differences taken in double
+        for (size_t t = 0; t < nt; ++t) {  // v0, e1 = v1 - v0, e2 = v2 - v0 (Triangle.fs:45-46), differences taken in double
             const double* q = sc.triangles.data() + 9 * t;
-            dst.push_back(Mk4<R>::make(q[0], q[1], q[2], w0));
-            dst.push_back(Mk4<R>::make(q[3] - q[0], q[4] - q[1], q[5] - q[2], w1));
-            dst.push_back(Mk4<R>::make(q[6] - q[0], q[7] - q[1], q[8] - q[2], 0));
-        };
-        for (size_t t = 0; t < nt; ++t) pushTri(tris, t, 0, 0);
-        // slot ids ride in the w components as reals: exact up to 2^24 in float
-        if (sizeof(R) == 4 && (L.bvh_tri.size() >= (1u << 24) || nt >= (1u << 24))) { st.release(); return fail(FTB_ERR_UNSUPPORTED, "more than 16M mesh triangles"); }
-        for (size_t k = 0; k < L.bvh_tri.size(); ++k) pushTri(btris, (size_t)L.bvh_tri[k], (double)L.bvh_seq[k], (double)L.bvh_tri[k]);
-        UP(roots, v.mesh_root) UP(box, v.bvh_box) UP(links, v.bvh_links) UP(btris, v.bvh_tris) UP(tris, v.tris)
+            tris.push_back(Mk4<R>::make(q[0], q[1], q[2], 0));
+            tris.push_back(Mk4<R>::make(q[3] - q[0], q[4] - q[1], q[5] - q[2], 0));
+            tris.push_back(Mk4<R>::make(q[6] - q[0], q[7] - q[1], q[8] - q[2], 0));
+        }
+        // slot ids ride in a row of reals: exact up to 2^24 in float
+        if (sizeof(R) == 4 && nt >= (1u << 24)) { st.release(); return fail(FTB_ERR_UNSUPPORTED, "more than 16M mesh triangles"); }
+        leaves.reserve(L.bvh_leaves.size() * kBvhLeafRows);
+        for (const BvhLeafBlock& b : L.bvh_leaves) {
+            double c[9][4];
+            for (int k = 0; k < 4; ++k) {
+                const double* q = b.tri[k] >= 0 ? sc.triangles.data() + 9 * (size_t)b.tri[k] : nullptr;
+                for (int j = 0; j < 3; ++j) {
+                    c[j][k] = q ? q[j] : 0.0;
+                    c[3 + j][k] = q ? q[3 + j] - q[j] : 0.0;
+                    c[6 + j][k] = q ? q[6 + j] - q[j] : 0.0;
+                }
+            }
+            for (int j = 0; j < 9; ++j) leaves.push_back(Mk4<R>::make(c[j][0], c[j][1], c[j][2], c[j][3]));
+            leaves.push_back(Mk4<R>::make(b.seq[0], b.seq[1], b.seq[2], b.seq[3]));
+            leaves.push_back(Mk4<R>::make(b.tri[0], b.tri[1], b.tri[2], b.tri[3]));
+            leaves.push_back(Mk4<R>::make(0, 0, 0, 0));
+        }
+        UP(roots, v.mesh_root) UP(nodes, v.bvh_nodes) UP(leaves, v.bvh_leaves) UP(tris, v.tris)
     }
     {
         std::vector<int2> li; std::vector<R4> la, lb, lc;
@@ -459,6 +435,10 @@ int uploadScene(const ftb_scene& sc, SceneStorage<R>& st)
         }
         UP(li, v.light_i) UP(la, v.light_a) UP(lb, v.light_b) UP(lc, v.light_c)
         v.n_lights = (int)sc.lights.size();
+    }
+    {  // the inverse of `rotate unitZ 180` (Cylinder.fs:27) exactly as Transform.matrix builds it (Transform.fs:60-69, CommonTypes.fs:98-99)
+        const double ang = -(180.0 * 1.0 * (3.14159265358979323846 / 180.0));
+        v.cyl_c = (R)std::cos(ang); v.cyl_s = (R)std::sin(ang);
     }
 #undef UP
     st.ready = true;
@@ -566,16 +546,16 @@ void fillStats(const Control& h, const ftb_scene& sc, ftb_stats* s)
 {
     const unsigned long long* c = h.stats;
     s->primary_rays += c[ST_PRIMARY]; s->shadow_rays += c[ST_SHADOW]; s->reflection_rays += c[ST_REFLECTION]; s->shaded_hits += c[ST_SHADED];
-    // device leaf kinds -> ftb_prim_kind slots.  The parts of a solidCylinder are counted as what
-    // they are on the device (2 circles + 1 open cylinder); a cube is one fused leaf.
-    static const int slot[9] = {FTB_PRIM_SPHERE, FTB_PRIM_PLANE, FTB_PRIM_SQUARE, FTB_PRIM_CIRCLE, FTB_PRIM_CYLINDER, FTB_PRIM_CONE, FTB_PRIM_CUBE, FTB_PRIM_TRIANGLE, FTB_PRIM_BSPMESH};
-    for (int k = 0; k < 9; ++k) s->leaf_tests[slot[k]] += c[ST_LEAF0 + k];
+    // device leaf kinds -> ftb_prim_kind slots.  A cube and a solidCylinder are one fused leaf each.
+    static const int slot[kLeafKinds] = {FTB_PRIM_SPHERE, FTB_PRIM_PLANE, FTB_PRIM_SQUARE, FTB_PRIM_CIRCLE, FTB_PRIM_CYLINDER, FTB_PRIM_CONE, FTB_PRIM_CUBE, FTB_PRIM_TRIANGLE, FTB_PRIM_BSPMESH,
+                                         FTB_PRIM_SOLIDCYLINDER};
+    for (int k = 0; k < kLeafKinds; ++k) s->leaf_tests[slot[k]] += c[ST_LEAF0 + k];
     s->leaf_tests[FTB_PRIM_TRIANGLE] += c[ST_TRI_TESTS_IN_MESH];
     s->transformed_leaf_tests += c[ST_XFORM]; s->bsp_nodes_visited += c[ST_BSP_NODES]; s->bound_tests += c[ST_BOUND_TESTS] + c[ST_BOUND_FAST]; s->csg_ops += c[ST_CSG_OPS];
     // algorithmic flops, SURVEY.md 8(d) table (FMA = 2; compares / selects = 0)
-    static const double F[9] = {28, 8, 8, 8, 26, 32, 20, 45, 0};
+    static const double F[kLeafKinds] = {28, 8, 8, 8, 26, 32, 20, 45, 0, 42};  // solidCylinder: side + 2 caps in one frame
     double f = 0;
-    for (int k = 0; k < 9; ++k) f += F[k] * (double)c[ST_LEAF0 + k];
+    for (int k = 0; k < kLeafKinds; ++k) f += F[k] * (double)c[ST_LEAF0 + k];
     f += 45.0 * (double)c[ST_TRI_TESTS_IN_MESH] + 33.0 * (double)c[ST_XFORM] + 12.0 * (double)c[ST_BSP_NODES] + 17.0 * (double)c[ST_BOUND_TESTS]   // bound test: 3 sub + 2 dot (5 each) + 2 FMA
          + 5.0 * (double)c[ST_BOUND_FAST];  // common-origin form: one dot
     f += (double)c[ST_SHADED] * (60.0 + 110.0 * (double)sc.lights.size()) + 18.0 * (double)c[ST_REFLECTION];
@@ -871,7 +851,7 @@ int ftb_scene_create(const ftb_scene_desc* desc, ftb_scene** out)
     int rc = ftb::lower_scene(*desc, sc->L, err);
     if (rc != FTB_OK) return fail(rc, err);
     if (sc->L.max_csg_lists > ftb::kMaxLists) return fail(FTB_ERR_UNSUPPORTED, "CSG nesting needs more than 12 pending hit lists");
-    if (sc->L.max_bvh_depth + 2 > ftb::kBspStack) return fail(FTB_ERR_UNSUPPORTED, "mesh index deeper than the 64-entry traversal stack");
+    if (sc->L.max_bvh_stack > ftb::kBspStack) return fail(FTB_ERR_UNSUPPORTED, "mesh index deeper than the 64-entry traversal stack");
     if (sc->L.leaves.size() >= (1u << 22)) return fail(FTB_ERR_UNSUPPORTED, "more than 4M leaves");
     sc->bsp_nodes.assign(desc->bsp_nodes, desc->bsp_nodes + desc->n_bsp_nodes);
     sc->bsp_leaves.assign(desc->bsp_leaves, desc->bsp_leaves + desc->n_bsp_leaves);
@@ -1041,19 +1021,14 @@ int ftb_render(ftb_scene* scene, const ftb_camera* camera, const ftb_render_para
     const size_t frameBytes = outBytes(&p);
     const size_t rowBytes = frameBytes / (size_t)p.height;
     // The frame is rendered in bands of tile rows, on every device; a finished band is assembled and sent to the host while
-    // the next bands render (the download of a 1080p f64 frame takes half as long as rendering it, and the CPU's own copy
-    // out of the page-locked ring as long again), so only the last, smallest band's copy is exposed.
-    static const bool noBands = std::getenv("FTB_NO_BANDS") != nullptr;  // A/B switch for measurements
-    const bool banded = !dbg && !stats && !full.corner && !noBands && (long long)p.width * p.height >= 262144 && full.tiles_y >= 8;
-    const int kBands = banded ? 4 : 1;
+    // the next bands render, so only the last, smallest band's copy is exposed.  Every band costs a kernel launch with its
+    // own tail, so small downloads use fewer bands: one band per 12 MB of frame, at most 4 (a 1080p RGBA8 frame goes in
+    // one piece, the same frame as f64 or an 8K RGBA8 frame in four).
+    static const int bandsEnv = [] { const char* e = std::getenv("FTB_BANDS"); return e ? std::atoi(e) : 0; }();  // A/B switch for measurements
+    const bool bandable = !dbg && !stats && !full.corner && (long long)p.width * p.height >= 262144 && full.tiles_y >= 8;
+    int kBands = 1;
+    if (bandable) kBands = bandsEnv > 0 ? std::min(bandsEnv, 4) : (int)std::min<size_t>(4, std::max<size_t>(1, frameBytes / (12u << 20)));
     const int primary = devs[0];
-    // A/B switch: page-lock the caller's buffer for the duration of the call instead of staging through the ring
-    static const bool hostRegister = std::getenv("FTB_HOST_REGISTER") != nullptr;
-    bool registered = false;
-    if (hostRegister && !HostCopier::pageLocked(out)) {
-        if (cudaHostRegister(out, frameBytes, cudaHostRegisterDefault) == cudaSuccess) registered = true; else (void)cudaGetLastError();
-    }
-    struct Unregister { void* p; bool on; ~Unregister() { if (on) cudaHostUnregister(p); } } unregister = {out, registered};
 
     struct Shard { PerDevice* pd; FrameGeom g; ftb_render_params ps; void* target; bool direct; };
     std::vector<Shard> sh((size_t)n_gpus);

@@ -10,7 +10,8 @@ namespace ftb {
 
 constexpr int kHitCap = 32;    // per-ray CSG hit stack entries
 constexpr int kMaxLists = 12;  // per-ray CSG list stack depth
-constexpr int kBspStack = 64;  // per-ray BSP traversal stack
+constexpr int kBspStack = 64;  // per-ray mesh traversal stack
+constexpr int kBvhNodeRows = 8, kBvhLeafRows = 12;
 constexpr int kBlockThreads = 128;
 // most samples of one unit of the blend ring (render.cuh): a launch covers at most this many samples per pixel,
 // frames with more are rendered in several passes that continue the same left fold
@@ -34,7 +35,7 @@ struct V4<double> {
 // rendered by the smallest compiled variant whose mask covers lower.h's Lowered::features.
 enum Feature : unsigned {
     FT_CUBE = 0x01,   // LEAF_CUBE
-    FT_ROUND = 0x02,  // LEAF_SQUARE, LEAF_CIRCLE, LEAF_CYLINDER, LEAF_CONE
+    FT_ROUND = 0x02,  // LEAF_SQUARE, LEAF_CIRCLE, LEAF_CYLINDER, LEAF_CONE, LEAF_SOLIDCYL
     FT_MESH = 0x04,   // LEAF_TRIANGLE, LEAF_MESH (BSP traversal)
     FT_CSG = 0x08,    // CSG items that are a binary op of two single leaves (evaluated in registers)
     FT_TEX = 0x10,    // grid / image textures, sphere uv
@@ -43,7 +44,8 @@ enum Feature : unsigned {
     FT_CSGN = 0x80,   // any other CSG item (general post-order program, inlined)
     FT_PLANAR = 0x100,  // a top-level plane / square / circle leaf exists (FP32 self-intersection guard, render.cuh)
     FT_TABLE = 0x200,  // enough top-level items for the common-origin bound table to pay (lower.h kFeatOriginTable, render.cuh)
-    FT_PAIRG = 0x400,  // a CSG pair (FT_CSG) whose operand is a run of leaves, e.g. solidCylinder (lower.cpp, render.cuh csgPair)
+    FT_PAIRG = 0x400,  // CSG pairs (FT_CSG) walk both operands through ONE copy of the leaf intersectors: scenes with many leaf kinds
+                       // (instruction footprint) and pairs whose operand is a run of leaves (lower.cpp, render.cuh csgPair)
     FT_ALL = 0x7ff
 };
 
@@ -52,8 +54,8 @@ enum StatSlot : int {
     ST_SHADOW,
     ST_REFLECTION,
     ST_SHADED,
-    ST_LEAF0,  // 9 leaf kinds follow (ftb::LeafKind order)
-    ST_XFORM = ST_LEAF0 + 9,
+    ST_LEAF0,  // 10 leaf kinds follow (ftb::LeafKind order)
+    ST_XFORM = ST_LEAF0 + 10,
     ST_BSP_NODES,
     ST_BOUND_TESTS,
     ST_CSG_OPS,
@@ -89,11 +91,14 @@ struct DevScene {
     const R* texop_ab;  // 2 per op
     const uchar4* texels;
     const int4* img_i;  // x = first texel, y = width, z = height
-    // meshes: the device's own BVH over each mesh's triangles (lower.h BvhNode)
-    const int* mesh_root;    // per mesh: root link (>= 0 node, < 0 ~((first << 3) | count))
-    const R4* bvh_box;       // 3 per node: (L.lo.xyz, L.hi.x) (L.hi.yz, R.lo.xy) (R.lo.z, R.hi.xyz)
-    const int2* bvh_links;   // per node: child links
-    const R4* bvh_tris;      // 3 per slot: (v0, seq) (e1, triangle index) (e2, -); the ints stored as reals
+    // meshes: the device's own 4-wide BVH over each mesh's triangles (lower.h Bvh4Node / BvhLeafBlock).  One node = kBvhNodeRows
+    // rows of R4 (128 B in FP32: one cache line), each row holding one quantity of the FOUR children: lo.x lo.y lo.z hi.x hi.y
+    // hi.z, then the child links as int bits (FP32) / as exact reals (FP64); one leaf block = kBvhLeafRows rows, one quantity
+    // of its FOUR triangle slots each: v0.x v0.y v0.z e1.x e1.y e1.z e2.x e2.y e2.z, enumeration rank, triangle index (-1 = empty
+    // slot), the two ints as exact reals.
+    const int* mesh_root;    // per mesh: root link (>= 0 node, < 0 ~(leaf block), kBvhNone = empty mesh)
+    const R4* bvh_nodes;
+    const R4* bvh_leaves;
     const R4* tris;          // 3 per scene triangle: v0, e1 = v1 - v0, e2 = v2 - v0 (LEAF_TRIANGLE, normals)
     // lights
     const int2* light_i;  // kind, samples
@@ -101,6 +106,7 @@ struct DevScene {
     const R4* light_b;    // falloff c, l, q
     const R4* light_c;    // colour
     int n_lights;
+    R cyl_c, cyl_s;  // cos / sin of the -180 degree rotation about z that puts the bottom cap of a solidCylinder in place (Cylinder.fs:27), as the host computes them
 };
 
 template <typename R>

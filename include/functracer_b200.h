@@ -243,8 +243,8 @@ typedef struct ftb_stats {
     uint64_t shadow_rays;
     uint64_t reflection_rays; /* unique reflection rays */
     uint64_t shaded_hits;
-    uint64_t leaf_tests[10];  /* by ftb_prim_kind; a cube counts once, the three parts of a solidCylinder count as
-                                 2 circles + 1 cylinder, mesh triangles tested count under FTB_PRIM_TRIANGLE */
+    uint64_t leaf_tests[10];  /* by ftb_prim_kind; a cube and a solidCylinder count once each, mesh triangles tested
+                                 count under FTB_PRIM_TRIANGLE */
     uint64_t transformed_leaf_tests;
     uint64_t bsp_nodes_visited; /* nodes of the device's mesh index (a BVH over the BSP's triangles) visited */
     uint64_t bound_tests;     /* object-level bound tests (no counterpart in the reference) */
@@ -271,11 +271,11 @@ void ftb_scene_destroy(ftb_scene* scene);
  * W*H pixels in params->out_format, row-major (y, then x), blended (Image.fs:112-116 /
  * 134-144) and un-clamped unless RGBA8.  dbg and stats may be NULL.
  *
- * out may be ordinary pageable memory (a GC-pinned .NET array, a std::vector, a numpy array): the frame is
- * rendered in bands of tile rows, every finished band travels device -> library-owned page-locked ring ->
- * out while the later bands render, so only the last band's copy is exposed.  CUDA page-locked memory
- * (cudaHostAlloc / cudaHostRegister) is detected and written directly.  FTB_OUT_RGBA8 is what Image.write
- * keeps of a frame (Image.fs:35-44: clamp, * 255, truncate) at 1/6 of the bytes of FTB_OUT_RGB_F64.
+ * out may be ordinary pageable memory (a GC-pinned .NET array, a std::vector, a numpy array) or CUDA
+ * page-locked memory: the frame is rendered in up to four bands of tile rows, ALL of them queued before
+ * the first byte is copied, and every finished band is downloaded while the later bands render, so only
+ * the last band's copy is exposed.  FTB_OUT_RGBA8 is what Image.write keeps of a frame (Image.fs:35-44:
+ * clamp, * 255, truncate) at 1/6 of the bytes of FTB_OUT_RGB_F64.
  *
  * One scene holds ONE frame in flight per device: the per-device scratch (tile queue counter, jitter table,
  * tile order) is shared by all calls on that scene; concurrent frames need separate ftb_scene objects. */
@@ -310,13 +310,12 @@ int ftb_band_rows(const ftb_render_params* params, int band_index, int band_coun
 int ftb_assemble_rows_device(const ftb_render_params* params, const void* const* d_tile_buffers,
                              void* d_out, int y0, int y1, void* stream);
 
-/* Device -> host copy that accepts pageable destinations at full link speed.  ftb_host_copy_begin queues
- * the copy of `bytes` from d_src (current device) behind the work already queued on `stream` and returns
- * without waiting for that work: page-locked destinations are written directly; pageable ones go through
- * the scene's page-locked ring (4 x 16 MB per device), the CPU copying finished pieces out while the
- * later ones are in flight.  Pieces that do not fit in the ring are completed inside the call (so queue all
- * rendering first, then begin the copies in the order the data becomes ready).  ftb_host_copy_finish
- * completes every pending copy of the scene on the current device; after it returns the data is in place. */
+/* Device -> host copy of a finished band behind the work already queued on `stream` (current device).
+ * A page-locked destination makes the call asynchronous; with a pageable one it returns when that band has
+ * arrived (the driver stages it at link speed) - so queue ALL rendering and assembly first, then begin the
+ * copies in the order the bands finish: the GPU renders band c + 1 while the host sits in the copy of band c.
+ * ftb_host_copy_finish waits for every copy begun on the scene for the current device; after it returns the
+ * data is in place. */
 int ftb_host_copy_begin(ftb_scene* scene, const void* d_src, void* host_dst, int64_t bytes, void* stream);
 int ftb_host_copy_finish(ftb_scene* scene);
 

@@ -5,7 +5,8 @@
   * final colour within 1/255 per channel on >= 99.9 % of the compared pixels, largest error printed (north_star's bar);
   * the primary primitive-id plane (one entry per SAMPLE) equal to the oracle's except at silhouettes / ties: every
     mismatching sample must carry an id that the oracle's own map shows within one pixel of it (oracle/parity.py) -
-    a missing object or a wrong occluder would not; mismatch counts are printed; sub-ids (cube face, cylinder part,
+    a missing object or a wrong occluder would not (the one other documented case, an FP32 ray leaking through the shared
+    edge of two mesh triangles, is recognised separately); mismatch counts are printed; sub-ids (cube face, cylinder part,
     mesh triangle) are compared where the primitive ids agree;
   * tile sharding is invisible (2 shards assembled == 1 shard, bit for bit) on the smaller configs;
   * the ray counts of the counting kernel satisfy the scene's invariants (one primary ray per sample; shadow rays <=
@@ -92,7 +93,7 @@ def test_full_size_config(name):
         m = parity.merge(parts)
         rec = dict(config=name, width=W, height=H, spp=spp, compared="whole frame" if name in WHOLE else "%d stripes of %d px" % (N_STRIPES, STRIPE_W),
                    pixels=m["pixels"], frac_within_1_255=m["frac_within_1_255"], max_err=m["max_err"], nonfinite_pixels=m["nonfinite"],
-                   primary_samples=m["samples"], prim_id_mismatches=m["prim_mismatch"], prim_id_unexplained=m["prim_unexplained"],
+                   primary_samples=m["samples"], prim_id_mismatches=m["prim_mismatch"], prim_id_unexplained=m["prim_unexplained"], prim_id_edge_leaks=m.get("prim_edge_leak", 0),
                    sub_id_mismatches=m.get("sub_mismatch", 0), rays=dict(primary=st.primary_rays, shadow=st.shadow_rays, reflection=st.reflection_rays),
                    cpu_oracle_mrays_s=cpu_rays / cpu_s / 1e6, cpu_threads=os.cpu_count())
         print(json.dumps(rec))
@@ -105,5 +106,5 @@ def test_full_size_config(name):
         assert m["nonfinite"] == 0
         assert m["frac_within_1_255"] >= 0.999
         assert m["prim_mismatch"] <= 2e-3 * m["samples"]
-        assert m["prim_unexplained"] == 0, "%d primary samples carry a primitive id the oracle does not show within one pixel" % m["prim_unexplained"]
+        assert m["prim_unexplained"] == 0, "%d primary samples carry a primitive id the oracle does not show within one pixel: %s" % (m["prim_unexplained"], m.get("unexplained_samples"))
         assert m.get("sub_mismatch", 0) <= 5e-3 * m["samples"]

@@ -325,9 +325,9 @@ def test_open_csg_operand_behind_the_origin_is_not_culled():
 
 
 def test_pageable_pinned_and_quantised_host_frames():
-    """ftb_render into ordinary pageable memory (what a P/Invoke caller passes) goes through the page-locked ring in
-    pieces, band by band; into CUDA page-locked memory directly.  Same bits either way, in every output format, and the
-    RGBA8 frame is Image.write's quantisation (Image.fs:36-40) of the f64 one."""
+    """ftb_render into ordinary pageable memory (what a P/Invoke caller passes) and into CUDA page-locked memory, band by
+    band: same bits either way, in every output format, and the RGBA8 frame is Image.write's quantisation (Image.fs:36-40)
+    of the f64 one."""
     import torch
     W, H, spp = 1100, 720, 1
     sc = parse(scenes.hollow_sphere(res=(W, H), spp=spp))
@@ -345,7 +345,7 @@ def test_pageable_pinned_and_quantised_host_frames():
             frames[fmt] = pageable
         assert (frames[abi.OUT_RGB_F32] == frames[abi.OUT_RGB_F64].astype(np.float32)).all()
         assert (frames[abi.OUT_RGBA8][..., :3] == orc.quantise(frames[abi.OUT_RGB_F32].astype(np.float64))).all()
-        # a frame larger than the 64 MB ring (pieces are recycled while the copy is in flight)
+        # a larger frame (four bands)
         W2, H2 = 2600, 1500  # 93.6 MB as f64
         big = np.zeros((H2, W2, 3), dtype=np.float64)
         scene.render(W2, H2, 1, jit, out_format=abi.OUT_RGB_F64, out=big)
