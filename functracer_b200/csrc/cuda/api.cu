@@ -293,16 +293,6 @@ template <typename R> struct Mk4;
 template <> struct Mk4<float> { static float4 make(double a, double b, double c, double d) { return make_float4((float)a, (float)b, (float)c, (float)d); } };
 template <> struct Mk4<double> { static double4 make(double a, double b, double c, double d) { return make_double4(a, b, c, d); } };
 
-// the four child links of a BVH node as one row: int bits in FP32 (a link does not fit a float's 24 bits), exact reals in FP64
-template <typename R> typename V4<R>::type linkRow(const int32_t* c);
-template <> float4 linkRow<float>(const int32_t* c)
-{
-    float4 r;
-    std::memcpy(&r.x, &c[0], 4); std::memcpy(&r.y, &c[1], 4); std::memcpy(&r.z, &c[2], 4); std::memcpy(&r.w, &c[3], 4);
-    return r;
-}
-template <> double4 linkRow<double>(const int32_t* c) { return make_double4((double)c[0], (double)c[1], (double)c[2], (double)c[3]); }
-
 template <typename T>
 int upload(std::vector<void*>& allocs, const std::vector<T>& host, const T*& dev)
 {
@@ -390,40 +380,31 @@ int uploadScene(const ftb_scene& sc, SceneStorage<R>& st)
         UP(texels, v.texels) UP(ii, v.img_i)
     }
     {
-        std::vector<int> roots(L.mesh_root.begin(), L.mesh_root.end()); std::vector<R4> nodes, leaves, tris;
-        nodes.reserve(L.bvh_nodes.size() * kBvhNodeRows);
-        for (const Bvh4Node& n : L.bvh_nodes) {
-            for (int a = 0; a < 3; ++a) nodes.push_back(sizeof(R) == 4 ? Mk4<R>::make(n.lo[a][0], n.lo[a][1], n.lo[a][2], n.lo[a][3]) : Mk4<R>::make(n.dlo[a][0], n.dlo[a][1], n.dlo[a][2], n.dlo[a][3]));
-            for (int a = 0; a < 3; ++a) nodes.push_back(sizeof(R) == 4 ? Mk4<R>::make(n.hi[a][0], n.hi[a][1], n.hi[a][2], n.hi[a][3]) : Mk4<R>::make(n.dhi[a][0], n.dhi[a][1], n.dhi[a][2], n.dhi[a][3]));
-            nodes.push_back(linkRow<R>(n.child));
-            nodes.push_back(Mk4<R>::make(0, 0, 0, 0));
+        std::vector<int> roots(L.mesh_root.begin(), L.mesh_root.end()); std::vector<int2> links; std::vector<R4> box, btris, tris;
+        for (const BvhNode& n : L.bvh_nodes) {
+            if (sizeof(R) == 4) {
+                box.push_back(Mk4<R>::make(n.lo[0][0], n.lo[0][1], n.lo[0][2], n.hi[0][0]));
+                box.push_back(Mk4<R>::make(n.hi[0][1], n.hi[0][2], n.lo[1][0], n.lo[1][1]));
+                box.push_back(Mk4<R>::make(n.lo[1][2], n.hi[1][0], n.hi[1][1], n.hi[1][2]));
+            } else {
+                box.push_back(Mk4<R>::make(n.dlo[0][0], n.dlo[0][1], n.dlo[0][2], n.dhi[0][0]));
+                box.push_back(Mk4<R>::make(n.dhi[0][1], n.dhi[0][2], n.dlo[1][0], n.dlo[1][1]));
+                box.push_back(Mk4<R>::make(n.dlo[1][2], n.dhi[1][0], n.dhi[1][1], n.dhi[1][2]));
+            }
+            links.push_back(make_int2(n.child[0], n.child[1]));
         }
         const size_t nt = sc.triangles.size() / 9;
-        for (size_t t = 0; t < nt; ++t) {  // v0, e1 = v1 - v0, e2 = v2 - v0 (Triangle.fs:45-46), differences taken in double
+        auto pushTri = [&](std::vector<R4>& dst, size_t t, double w0, double w1) {  // v0, e1 = v1 - v0, e2 = v2 - v0 (Triangle.fs:45-46), differences taken in double
             const double* q = sc.triangles.data() + 9 * t;
-            tris.push_back(Mk4<R>::make(q[0], q[1], q[2], 0));
-            tris.push_back(Mk4<R>::make(q[3] - q[0], q[4] - q[1], q[5] - q[2], 0));
-            tris.push_back(Mk4<R>::make(q[6] - q[0], q[7] - q[1], q[8] - q[2], 0));
-        }
-        // slot ids ride in a row of reals: exact up to 2^24 in float
-        if (sizeof(R) == 4 && nt >= (1u << 24)) { st.release(); return fail(FTB_ERR_UNSUPPORTED, "more than 16M mesh triangles"); }
-        leaves.reserve(L.bvh_leaves.size() * kBvhLeafRows);
-        for (const BvhLeafBlock& b : L.bvh_leaves) {
-            double c[9][4];
-            for (int k = 0; k < 4; ++k) {
-                const double* q = b.tri[k] >= 0 ? sc.triangles.data() + 9 * (size_t)b.tri[k] : nullptr;
-                for (int j = 0; j < 3; ++j) {
-                    c[j][k] = q ? q[j] : 0.0;
-                    c[3 + j][k] = q ? q[3 + j] - q[j] : 0.0;
-                    c[6 + j][k] = q ? q[6 + j] - q[j] : 0.0;
-                }
-            }
-            for (int j = 0; j < 9; ++j) leaves.push_back(Mk4<R>::make(c[j][0], c[j][1], c[j][2], c[j][3]));
-            leaves.push_back(Mk4<R>::make(b.seq[0], b.seq[1], b.seq[2], b.seq[3]));
-            leaves.push_back(Mk4<R>::make(b.tri[0], b.tri[1], b.tri[2], b.tri[3]));
-            leaves.push_back(Mk4<R>::make(0, 0, 0, 0));
-        }
-        UP(roots, v.mesh_root) UP(nodes, v.bvh_nodes) UP(leaves, v.bvh_leaves) UP(tris, v.tris)
+            dst.push_back(Mk4<R>::make(q[0], q[1], q[2], w0));
+            dst.push_back(Mk4<R>::make(q[3] - q[0], q[4] - q[1], q[5] - q[2], w1));
+            dst.push_back(Mk4<R>::make(q[6] - q[0], q[7] - q[1], q[8] - q[2], 0));
+        };
+        for (size_t t = 0; t < nt; ++t) pushTri(tris, t, 0, 0);
+        // slot ids ride in the w components as reals: exact up to 2^24 in float
+        if (sizeof(R) == 4 && (L.bvh_tri.size() >= (1u << 24) || nt >= (1u << 24))) { st.release(); return fail(FTB_ERR_UNSUPPORTED, "more than 16M mesh triangles"); }
+        for (size_t k = 0; k < L.bvh_tri.size(); ++k) pushTri(btris, (size_t)L.bvh_tri[k], (double)L.bvh_seq[k], (double)L.bvh_tri[k]);
+        UP(roots, v.mesh_root) UP(box, v.bvh_box) UP(links, v.bvh_links) UP(btris, v.bvh_tris) UP(tris, v.tris)
     }
     {
         std::vector<int2> li; std::vector<R4> la, lb, lc;
@@ -851,7 +832,7 @@ int ftb_scene_create(const ftb_scene_desc* desc, ftb_scene** out)
     int rc = ftb::lower_scene(*desc, sc->L, err);
     if (rc != FTB_OK) return fail(rc, err);
     if (sc->L.max_csg_lists > ftb::kMaxLists) return fail(FTB_ERR_UNSUPPORTED, "CSG nesting needs more than 12 pending hit lists");
-    if (sc->L.max_bvh_stack > ftb::kBspStack) return fail(FTB_ERR_UNSUPPORTED, "mesh index deeper than the 64-entry traversal stack");
+    if (sc->L.max_bvh_depth + 2 > ftb::kBspStack) return fail(FTB_ERR_UNSUPPORTED, "mesh index deeper than the 64-entry traversal stack");
     if (sc->L.leaves.size() >= (1u << 22)) return fail(FTB_ERR_UNSUPPORTED, "more than 4M leaves");
     sc->bsp_nodes.assign(desc->bsp_nodes, desc->bsp_nodes + desc->n_bsp_nodes);
     sc->bsp_leaves.assign(desc->bsp_leaves, desc->bsp_leaves + desc->n_bsp_leaves);
@@ -1021,13 +1002,11 @@ int ftb_render(ftb_scene* scene, const ftb_camera* camera, const ftb_render_para
     const size_t frameBytes = outBytes(&p);
     const size_t rowBytes = frameBytes / (size_t)p.height;
     // The frame is rendered in bands of tile rows, on every device; a finished band is assembled and sent to the host while
-    // the next bands render, so only the last, smallest band's copy is exposed.  Every band costs a kernel launch with its
-    // own tail, so small downloads use fewer bands: one band per 12 MB of frame, at most 4 (a 1080p RGBA8 frame goes in
-    // one piece, the same frame as f64 or an 8K RGBA8 frame in four).
+    // the next bands render, so only the last, smallest band's copy is exposed.  Four bands also for small downloads: a 1080p
+    // RGBA8 frame (8 MB) measured 1.44 ms with four bands against 1.71 ms in one piece (hollow-sphere, 1.17 ms device-resident).
     static const int bandsEnv = [] { const char* e = std::getenv("FTB_BANDS"); return e ? std::atoi(e) : 0; }();  // A/B switch for measurements
     const bool bandable = !dbg && !stats && !full.corner && (long long)p.width * p.height >= 262144 && full.tiles_y >= 8;
-    int kBands = 1;
-    if (bandable) kBands = bandsEnv > 0 ? std::min(bandsEnv, 4) : (int)std::min<size_t>(4, std::max<size_t>(1, frameBytes / (12u << 20)));
+    const int kBands = bandable ? (bandsEnv > 0 ? std::min(bandsEnv, 4) : 4) : 1;
     const int primary = devs[0];
 
     struct Shard { PerDevice* pd; FrameGeom g; ftb_render_params ps; void* target; bool direct; };

@@ -11,7 +11,6 @@ namespace ftb {
 constexpr int kHitCap = 32;    // per-ray CSG hit stack entries
 constexpr int kMaxLists = 12;  // per-ray CSG list stack depth
 constexpr int kBspStack = 64;  // per-ray mesh traversal stack
-constexpr int kBvhNodeRows = 8, kBvhLeafRows = 12;
 constexpr int kBlockThreads = 128;
 // most samples of one unit of the blend ring (render.cuh): a launch covers at most this many samples per pixel,
 // frames with more are rendered in several passes that continue the same left fold
@@ -91,14 +90,11 @@ struct DevScene {
     const R* texop_ab;  // 2 per op
     const uchar4* texels;
     const int4* img_i;  // x = first texel, y = width, z = height
-    // meshes: the device's own 4-wide BVH over each mesh's triangles (lower.h Bvh4Node / BvhLeafBlock).  One node = kBvhNodeRows
-    // rows of R4 (128 B in FP32: one cache line), each row holding one quantity of the FOUR children: lo.x lo.y lo.z hi.x hi.y
-    // hi.z, then the child links as int bits (FP32) / as exact reals (FP64); one leaf block = kBvhLeafRows rows, one quantity
-    // of its FOUR triangle slots each: v0.x v0.y v0.z e1.x e1.y e1.z e2.x e2.y e2.z, enumeration rank, triangle index (-1 = empty
-    // slot), the two ints as exact reals.
-    const int* mesh_root;    // per mesh: root link (>= 0 node, < 0 ~(leaf block), kBvhNone = empty mesh)
-    const R4* bvh_nodes;
-    const R4* bvh_leaves;
+    // meshes: the device's own BVH over each mesh's triangles (lower.h BvhNode)
+    const int* mesh_root;    // per mesh: root link (>= 0 node, < 0 ~((first << 3) | count))
+    const R4* bvh_box;       // 3 per node: (L.lo.xyz, L.hi.x) (L.hi.yz, R.lo.xy) (R.lo.z, R.hi.xyz)
+    const int2* bvh_links;   // per node: child links
+    const R4* bvh_tris;      // 3 per slot: (v0, seq) (e1, triangle index) (e2, -); the ints stored as reals
     const R4* tris;          // 3 per scene triangle: v0, e1 = v1 - v0, e2 = v2 - v0 (LEAF_TRIANGLE, normals)
     // lights
     const int2* light_i;  // kind, samples

@@ -465,7 +465,7 @@ struct Lowerer {
 
 namespace {
 
-// ---- BVH over a mesh's triangles: binned SAH binary build (leaves of <= 4 triangles), then collapsed to 4-wide ----------
+// ---- BVH over a mesh's triangles (binned SAH, leaves of <= 4 triangles) ---------------------------------------
 struct Box {
     double lo[3], hi[3];
     void reset() { for (int k = 0; k < 3; ++k) { lo[k] = 1e300; hi[k] = -1e300; } }
@@ -480,17 +480,15 @@ struct Box {
 };
 
 struct BvhBuilder {
-    // the binary tree: children >= 0 inner node, < 0 ~(first | count << 28) a run of <= 4 refs
-    struct Node2 { int child[2]; Box box[2]; };
-    std::vector<Node2> nodes2;
+    const double* tris;            // scene triangles, 9 doubles each
     std::vector<int32_t> ref;      // triangle indices being partitioned
     std::vector<Box> tbox;         // per ref position
     std::vector<double> cen;       // 3 per ref position
-    const std::vector<int32_t>& seqOf;
     Lowered& L;
-    int maxStack = 0;
+    int slotBase;
+    int maxDepth = 0;
 
-    BvhBuilder(Lowered& l, const std::vector<int32_t>& seq) : seqOf(seq), L(l) {}
+    BvhBuilder(const double* t, Lowered& l) : tris(t), L(l), slotBase(0) {}
 
     Box boxOf(int b, int e) const
     {
@@ -505,9 +503,15 @@ struct BvhBuilder {
     }
     int build(int b, int e, int depth)
     {
+        maxDepth = std::max(maxDepth, depth);
         const int n = e - b;
-        if (n <= 4) return ~(b | (n << 28));
-        if (depth >= 60) return makeNode(b, b + n / 2, e, depth);  // degenerate input: halve until the runs fit
+        if (n <= 4 || depth >= 60) {
+            if (n > 7) {  // depth cap with a fat run: split it into a chain so that every leaf holds <= 4 (count has 3 bits)
+                const int mid = b + 4;
+                return makeNode(b, mid, e, depth);
+            }
+            return ~(((slotBase + b) << 3) | n);
+        }
         Box cb; cb.reset();
         for (int i = b; i < e; ++i) cb.add(&cen[3 * i]);
         int axis = 0;
@@ -538,64 +542,29 @@ struct BvhBuilder {
                 mid = i;
             }
         }
-        if (mid <= b || mid >= e) mid = b + n / 2;  // all centroids coincide (or SAH found nothing): split the run in half
+        if (mid <= b || mid >= e) {  // all centroids coincide (or SAH found nothing): split the run in half
+            mid = b + n / 2;
+        }
         return makeNode(b, mid, e, depth);
     }
     int makeNode(int b, int mid, int e, int depth)
     {
-        const int idx = (int)nodes2.size();
-        nodes2.push_back(Node2());
+        const int idx = (int)L.bvh_nodes.size();
+        L.bvh_nodes.push_back(BvhNode());
         const int l = build(b, mid, depth + 1);
         const int r = build(mid, e, depth + 1);
-        nodes2[idx].child[0] = l; nodes2[idx].child[1] = r;
-        nodes2[idx].box[0] = boxOf(b, mid); nodes2[idx].box[1] = boxOf(mid, e);
-        return idx;
-    }
-
-    // ---- collapse: a 4-wide node takes a binary node's two children and keeps replacing the inner child with the largest
-    // box by its own two children until four slots are filled (or only leaves remain)
-    int emitLeaf(int link2)
-    {
-        const int code = ~link2, first = code & 0x0fffffff, count = code >> 28;
-        BvhLeafBlock blk;
-        for (int k = 0; k < 4; ++k) { blk.tri[k] = k < count ? ref[first + k] : -1; blk.seq[k] = k < count ? seqOf[ref[first + k]] : 0; }
-        L.bvh_leaves.push_back(blk);
-        return ~((int)L.bvh_leaves.size() - 1);
-    }
-    int collapse(int link2, int& stackNeed)
-    {
-        if (link2 < 0) { stackNeed = 0; return emitLeaf(link2); }
-        int links[4]; Box boxes[4]; int n = 2;
-        links[0] = nodes2[link2].child[0]; links[1] = nodes2[link2].child[1];
-        boxes[0] = nodes2[link2].box[0]; boxes[1] = nodes2[link2].box[1];
-        while (n < 4) {
-            int pick = -1;
-            double bestArea = -1;
-            for (int k = 0; k < n; ++k) if (links[k] >= 0 && boxes[k].area() > bestArea) { bestArea = boxes[k].area(); pick = k; }
-            if (pick < 0) break;
-            const Node2 nd = nodes2[links[pick]];
-            links[pick] = nd.child[0]; boxes[pick] = nd.box[0];
-            links[n] = nd.child[1]; boxes[n] = nd.box[1];
-            ++n;
-        }
-        const int idx = (int)L.bvh_nodes.size();
-        L.bvh_nodes.push_back(Bvh4Node());
-        int need = 0;
-        int out[4];
-        for (int k = 0; k < n; ++k) { int s = 0; out[k] = collapse(links[k], s); need = std::max(need, s); }
-        stackNeed = need + (n - 1);  // the siblings postponed while the deepest child is walked
-        Bvh4Node& nd = L.bvh_nodes[idx];
-        for (int k = 0; k < 4; ++k) {
-            nd.child[k] = k < n ? out[k] : kBvhNone;
-            for (int a = 0; a < 3; ++a) {
-                const double lo = k < n ? boxes[k].lo[a] : 0.0, hi = k < n ? boxes[k].hi[a] : 0.0;
-                nd.dlo[a][k] = lo; nd.dhi[a][k] = hi;
-                float flo = (float)lo, fhi = (float)hi;  // round outward
-                if ((double)flo > lo) flo = std::nextafterf(flo, -INFINITY);
-                if ((double)fhi < hi) fhi = std::nextafterf(fhi, INFINITY);
-                nd.lo[a][k] = flo; nd.hi[a][k] = fhi;
+        const Box lb = boxOf(b, mid), rb = boxOf(mid, e);
+        BvhNode& nd = L.bvh_nodes[idx];
+        nd.child[0] = l; nd.child[1] = r;
+        const Box* bx[2] = {&lb, &rb};
+        for (int c = 0; c < 2; ++c)
+            for (int k = 0; k < 3; ++k) {
+                nd.dlo[c][k] = bx[c]->lo[k]; nd.dhi[c][k] = bx[c]->hi[k];
+                float flo = (float)bx[c]->lo[k], fhi = (float)bx[c]->hi[k];  // round outward
+                if ((double)flo > bx[c]->lo[k]) flo = std::nextafterf(flo, -INFINITY);
+                if ((double)fhi < bx[c]->hi[k]) fhi = std::nextafterf(fhi, INFINITY);
+                nd.lo[c][k] = flo; nd.hi[c][k] = fhi;
             }
-        }
         return idx;
     }
 };
@@ -615,15 +584,15 @@ void enumerateBsp(const ftb_scene_desc& d, int link, std::vector<int32_t>& out, 
 
 void buildMeshIndex(const ftb_scene_desc& d, Lowered& L)
 {
-    L.mesh_root.assign((size_t)std::max(0, d.n_meshes), kBvhNone);
+    L.mesh_root.assign((size_t)std::max(0, d.n_meshes), ~0);
     for (int m = 0; m < d.n_meshes; ++m) {
         std::vector<int32_t> tri;
         if ((size_t)m < L.mesh_used.size() && L.mesh_used[m]) enumerateBsp(d, d.meshes[m].root, tri, 0);
-        const int n = (int)tri.size();
-        if (n == 0) continue;
-        std::vector<int32_t> seqOf((size_t)std::max(1, d.n_triangles), 0);
-        BvhBuilder bb(L, seqOf);
+        BvhBuilder bb(d.triangles, L);
+        bb.slotBase = (int)L.bvh_tri.size();
         bb.ref = tri;
+        const int n = (int)tri.size();
+        std::vector<int32_t> seqOf((size_t)std::max(1, d.n_triangles), 0);
         bb.tbox.resize(n); bb.cen.resize(3 * (size_t)n);
         for (int i = 0; i < n; ++i) {
             const double* t = d.triangles + 9 * (size_t)tri[i];
@@ -632,10 +601,9 @@ void buildMeshIndex(const ftb_scene_desc& d, Lowered& L)
             for (int k = 0; k < 3; ++k) bb.cen[3 * i + k] = 0.5 * (bb.tbox[i].lo[k] + bb.tbox[i].hi[k]);
             seqOf[tri[i]] = i;
         }
-        const int root2 = bb.build(0, n, 0);
-        int need = 0;
-        L.mesh_root[m] = bb.collapse(root2, need);
-        L.max_bvh_stack = std::max(L.max_bvh_stack, need + 1);
+        L.mesh_root[m] = n == 0 ? ~0 : bb.build(0, n, 0);
+        for (int i = 0; i < n; ++i) { L.bvh_tri.push_back(bb.ref[i]); L.bvh_seq.push_back(seqOf[bb.ref[i]]); }
+        L.max_bvh_depth = std::max(L.max_bvh_depth, bb.maxDepth);
     }
 }
 

@@ -111,30 +111,23 @@ struct CsgOp {
 // The device-side index over a mesh's triangles.  BspMesh.intersect (BspMesh.fs:67-76) visits every branch
 // whose AABB the ray's line touches, right subtree before left, and Scene.closest then keeps the smallest
 // t >= 0, first in that order on ties.  Which triangle that is does not depend on the shape of the tree,
-// only on the triangle set and on the enumeration order; so the device traverses its own 4-wide BVH (built
+// only on the triangle set and on the enumeration order; so the device traverses its own BVH (built here
 // over the same - already clipped - triangles, front to back, culling against the best t so far) and
 // breaks ties by `seq`, the triangle's rank in the reference's right-before-left enumeration.
-constexpr int32_t kBvhNone = 0x7fffffff;  // an empty child slot / an empty mesh
-
-struct Bvh4Node {
-    float lo[3][4];    // [axis][child]: child boxes, rounded outward from the double-precision triangle bounds
-    float hi[3][4];
-    int32_t child[4];  // >= 0: node index; < 0: ~(leaf block index); kBvhNone: empty slot
-    double dlo[3][4], dhi[3][4];  // the same boxes in double for the FP64 verification build
-};
-
-// Up to four triangles that the kernel tests together, branch-free (structure of arrays on the device).
-struct BvhLeafBlock {
-    int32_t tri[4];  // index into the scene's triangles[]; -1 = empty slot
-    int32_t seq[4];  // enumeration rank within the mesh
+struct BvhNode {
+    float lo[2][3];  // child boxes, rounded outward from the double-precision triangle bounds
+    float hi[2][3];
+    int32_t child[2];  // >= 0: node index; < 0: ~((first << 3) | count), a run of `count` <= 4 slots in bvh_tri
+    double dlo[2][3], dhi[2][3];  // the same boxes in double for the FP64 verification build
 };
 
 struct Lowered {
-    std::vector<Bvh4Node> bvh_nodes;
-    std::vector<BvhLeafBlock> bvh_leaves;
-    std::vector<int32_t> mesh_root;  // per mesh: link of the root (same encoding as Bvh4Node::child)
+    std::vector<BvhNode> bvh_nodes;
+    std::vector<int32_t> bvh_tri;    // slot -> index into the scene's triangles[]
+    std::vector<int32_t> bvh_seq;    // slot -> enumeration rank within its mesh
+    std::vector<int32_t> mesh_root;  // per mesh: link of the root (same encoding as BvhNode::child)
     std::vector<char> mesh_used;     // per mesh: referenced (and validated) by a bspMesh primitive
-    int32_t max_bvh_stack = 0;       // traversal stack entries the deepest mesh index can need
+    int32_t max_bvh_depth = 0;
     std::vector<Leaf> leaves;
     std::vector<Surface> surfaces;
     std::vector<TexOp> tex_ops;

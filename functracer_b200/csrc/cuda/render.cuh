@@ -292,115 +292,62 @@ FTB_DEV R boxEntry(R lx, R ly, R lz, R hx, R hy, R hz, const Vec<R>& o, const Ve
     return tn <= tf ? tn : inf_<R>();
 }
 
-// Triangle.fs:43-66 once more, without early exits, for the four-slot leaf blocks of the mesh index: the same operations in
-// the same order (so a hit has the same t as triangleT gives), the rejections folded into one flag.  Like the original's
-// comparisons, a NaN u or v rejects nothing by itself; the final t > epsilon does.
-template <typename R>
-FTB_DEV bool triangleFlag(Vec<R> v0, Vec<R> edge1, Vec<R> edge2, const Ray<R>& ray, R& t)
-{
-    const R epsilon = R(0.0000001);
-    const Vec<R> h = cross(ray.d, edge2);
-    const R a = dot(edge1, h);
-    bool ok = !(a > -epsilon && a < epsilon);
-    const R f = R(1) / a;
-    const Vec<R> s = ray.o - v0;
-    const R u = f * dot(s, h);
-    ok = ok && !(u < R(0) || u > R(1));
-    const Vec<R> q = cross(s, edge1);
-    const R v = dot(f * ray.d, q);
-    ok = ok && !(v < R(0) || u + v > R(1));
-    t = dot(f * edge2, q);
-    return ok && t > epsilon;
-}
-
-FTB_DEV int linkOf(float v) { return __float_as_int(v); }  // child links of a BVH node: int bits in FP32 ...
-FTB_DEV int linkOf(double v) { return (int)v; }            // ... exact reals in FP64 (api.cu linkRow)
-FTB_DEV int pick4(int4 v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
-
-// Nearest / any hit of a mesh (Scene.fs:9 BspMesh): the device's 4-wide BVH over the mesh's triangles, front to back,
+// Nearest / any hit of a mesh (Scene.fs:9 BspMesh): the device's BVH over the mesh's triangles, front to back,
 // culled against the best t so far.  Result = BspMesh.intersect (BspMesh.fs:67-76) followed by Scene.closest
 // (Scene.fs:112-116): smallest t, and among equal t the triangle that comes first in the reference's
 // right-before-left enumeration (`seq`).  limit: only hits with t < limit count (ties with earlier items lose).
-//   One step = one node = one 128-byte line holding the boxes of four children (seven LDG.128 issued together), the four
-//   entry distances sorted with integer min / max on their bit patterns (the child number in the two lowest bits), the
-//   nearest child walked next and the others postponed nearest-on-top; a leaf = four triangle slots tested without a
-//   branch.  Against the binary tree this halves the chain of dependent fetches and the stack traffic per ray.
-//   The stack cannot overflow: ftb_scene_create rejects a mesh whose index could need more than kBspStack entries.
 template <typename R, bool STATS>
-FTB_DEV bool intersectMesh(const DevScene<R>& S, int root, const Ray<R>& r, R limit, bool any, R& bt, int& btri, Counters<STATS>& cn)
+FTB_DEV bool intersectMesh(const DevScene<R>& S, int root, const Ray<R>& r, R limit, bool any, R& bt, int& btri, bool& overflow, Counters<STATS>& cn)
 {
     typedef typename V4<R>::type R4;
     int stack[kBspStack];
     R stackT[kBspStack];
     int sp = 0;
+    int link = root;
     bt = limit;
     btri = -1;
-    if (root == kBvhNone) return false;
-    int link = root;
     int bseq = 0x7fffffff;
     const Vec<R> inv = mk<R>(R(1) / r.d.x, R(1) / r.d.y, R(1) / r.d.z);
     for (;;) {
-        // ---- descend: inner nodes until a leaf block is reached ------------------------------------------------------
+        // ---- descend: inner nodes until a leaf is reached (every lane of the warp is doing box tests here) ----
         while (link >= 0) {
-            const R4* n = S.bvh_nodes + (size_t)kBvhNodeRows * (size_t)link;
-            const R4 lx = ldg4<R>(n), ly = ldg4<R>(n + 1), lz = ldg4<R>(n + 2), hx = ldg4<R>(n + 3), hy = ldg4<R>(n + 4), hz = ldg4<R>(n + 5), lk = ldg4<R>(n + 6);
-            const int4 ch = make_int4(linkOf(lk.x), linkOf(lk.y), linkOf(lk.z), linkOf(lk.w));
-            const R t0 = ch.x != kBvhNone ? boxEntry<R>(lx.x, ly.x, lz.x, hx.x, hy.x, hz.x, r.o, inv, bt) : inf_<R>();
-            const R t1 = ch.y != kBvhNone ? boxEntry<R>(lx.y, ly.y, lz.y, hx.y, hy.y, hz.y, r.o, inv, bt) : inf_<R>();
-            const R t2 = ch.z != kBvhNone ? boxEntry<R>(lx.z, ly.z, lz.z, hx.z, hy.z, hz.z, r.o, inv, bt) : inf_<R>();
-            const R t3 = ch.w != kBvhNone ? boxEntry<R>(lx.w, ly.w, lz.w, hx.w, hy.w, hz.w, r.o, inv, bt) : inf_<R>();
-            cn.add(ST_BSP_NODES, (ch.x != kBvhNone) + (ch.y != kBvhNone) + (ch.z != kBvhNone) + (ch.w != kBvhNone));  // box tests
-            if constexpr (sizeof(R) == 4) {
-                // entry distances are >= 0, so their bit patterns order like the floats; the two lowest mantissa bits carry
-                // the child number (the distance a postponed child is culled with is rounded DOWN by that: conservative)
-                constexpr int kMiss = 0x7f800000;
-                int k0 = (__float_as_int(t0) & ~3) | 0, k1 = (__float_as_int(t1) & ~3) | 1, k2 = (__float_as_int(t2) & ~3) | 2, k3 = (__float_as_int(t3) & ~3) | 3;
-                int a;
-                a = min(k0, k1); k1 = max(k0, k1); k0 = a;
-                a = min(k2, k3); k3 = max(k2, k3); k2 = a;
-                a = min(k0, k2); k2 = max(k0, k2); k0 = a;
-                a = min(k1, k3); k3 = max(k1, k3); k1 = a;
-                a = min(k1, k2); k2 = max(k1, k2); k1 = a;
-                if (k3 < kMiss) { stack[sp] = pick4(ch, k3 & 3); stackT[sp] = __int_as_float(k3 & ~3); ++sp; }
-                if (k2 < kMiss) { stack[sp] = pick4(ch, k2 & 3); stackT[sp] = __int_as_float(k2 & ~3); ++sp; }
-                if (k1 < kMiss) { stack[sp] = pick4(ch, k1 & 3); stackT[sp] = __int_as_float(k1 & ~3); ++sp; }
-                if (k0 < kMiss) link = pick4(ch, k0 & 3);
-                else { link = kBvhNone; break; }  // nothing below: pop
+            cn.add(ST_BSP_NODES);
+            const R4 b0 = ldg4<R>(S.bvh_box + 3 * link), b1 = ldg4<R>(S.bvh_box + 3 * link + 1), b2 = ldg4<R>(S.bvh_box + 3 * link + 2);
+            const int2 ch = __ldg(S.bvh_links + link);
+            const R tl = boxEntry<R>(b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, r.o, inv, bt);
+            const R tr = boxEntry<R>(b1.z, b1.w, b2.x, b2.y, b2.z, b2.w, r.o, inv, bt);
+            const bool hl = tl < inf_<R>(), hr = tr < inf_<R>();
+            if (hl && hr) {
+                const bool leftFirst = tl <= tr;
+                if (sp < kBspStack) { stack[sp] = leftFirst ? ch.y : ch.x; stackT[sp] = leftFirst ? tr : tl; ++sp; } else overflow = true;
+                link = leftFirst ? ch.x : ch.y;
+            } else if (hl || hr) {
+                link = hl ? ch.x : ch.y;
             } else {
-                R t[4] = {t0, t1, t2, t3};
-                int l[4] = {ch.x, ch.y, ch.z, ch.w};
-                auto cx = [&](int i, int j) { if (t[j] < t[i]) { const R tt = t[i]; t[i] = t[j]; t[j] = tt; const int ll = l[i]; l[i] = l[j]; l[j] = ll; } };
-                cx(0, 1); cx(2, 3); cx(0, 2); cx(1, 3); cx(1, 2);
-#pragma unroll
-                for (int k = 3; k >= 1; --k) if (t[k] < inf_<R>()) { stack[sp] = l[k]; stackT[sp] = t[k]; ++sp; }
-                if (t[0] < inf_<R>()) link = l[0];
-                else { link = kBvhNone; break; }
+                link = 0x7fffffff;  // nothing below: pop
+                break;
             }
         }
-        // ---- leaf block: four triangle slots, no branch -------------------------------------------------------------------
+        // ---- leaf: a run of <= 7 triangles ---------------------------------------------------------------------------
         if (link < 0) {
-            const R4* rows = S.bvh_leaves + (size_t)kBvhLeafRows * (size_t)(~link);
-            const R4 ax = ldg4<R>(rows), ay = ldg4<R>(rows + 1), az = ldg4<R>(rows + 2), bx = ldg4<R>(rows + 3), by = ldg4<R>(rows + 4), bz = ldg4<R>(rows + 5);
-            const R4 cx = ldg4<R>(rows + 6), cy = ldg4<R>(rows + 7), cz = ldg4<R>(rows + 8), sq = ldg4<R>(rows + 9), ti = ldg4<R>(rows + 10);
-#define FTB_SLOT(c)                                                                                                   \
-            {                                                                                                         \
-                R t;                                                                                                  \
-                const bool ok = triangleFlag<R>(mk<R>(ax.c, ay.c, az.c), mk<R>(bx.c, by.c, bz.c), mk<R>(cx.c, cy.c, cz.c), r, t) && ti.c >= R(0); \
-                const int seq = (int)sq.c;                                                                            \
-                cn.add(ST_TRI_TESTS_IN_MESH, ti.c >= R(0) ? 1u : 0u);                                                 \
-                if (ok && (t < bt || (t == bt && btri >= 0 && seq < bseq))) { bt = t; bseq = seq; btri = (int)ti.c; } \
+            const int code = ~link, first = code >> 3, count = code & 7;
+            for (int i = 0; i < count; ++i) {
+                R t; R4 a0, a1;
+                cn.add(ST_TRI_TESTS_IN_MESH);
+                if (triangleT<R>(S.bvh_tris + 3 * (first + i), r, t, a0, a1)) {
+                    const int seq = (int)a0.w;
+                    if (t < bt || (t == bt && btri >= 0 && seq < bseq)) { bt = t; bseq = seq; btri = (int)a1.w; }
+                }
             }
-            FTB_SLOT(x) FTB_SLOT(y) FTB_SLOT(z) FTB_SLOT(w)
-#undef FTB_SLOT
             if (any && btri >= 0) return true;
         }
         // ---- pop the nearest postponed subtree that can still hold a closer (or tying) hit -------------------------
-        link = kBvhNone;
+        link = 0x7fffffff;
         while (sp > 0) {
             --sp;
             if (stackT[sp] <= bt) { link = stack[sp]; break; }
         }
-        if (link == kBvhNone) break;
+        if (link == 0x7fffffff) break;
     }
     return btri >= 0;
 }
@@ -525,7 +472,7 @@ FTB_DEV void intersectLeaf(const DevScene<R>& S, int leaf, const Ray<R>& wr, Sin
         if constexpr (Sink::kIsRay) {
             if (kind == LEAF_MESH) {
                 R bt; int btri;
-                if (intersectMesh<R, STATS>(S, __ldg(S.mesh_root + meta.w), r, sink.limit, sink.any, bt, btri, cn)) sink.hit(bt, btri);
+                if (intersectMesh<R, STATS>(S, __ldg(S.mesh_root + meta.w), r, sink.limit, sink.any, bt, btri, sink.overflow, cn)) sink.hit(bt, btri);
                 return;
             }
         }
