@@ -215,6 +215,7 @@ class Runner:
         t0 = time.perf_counter()
         self.scene = api.Scene(self.parsed)
         self.create_ms = 1e3 * (time.perf_counter() - t0)
+        self.build = self.scene.build_info()  # mesh index: built on the device (PLOC) or on the host, and how long it took
         self.p_f32 = self.params(out_format=abi.OUT_RGB_F32)
         self.tiles = torch.empty(api.tile_buffer_bytes(self.p_f32), dtype=torch.uint8, device=dev)
         st = self.scene.render_tiles_device(self.params(out_format=abi.OUT_RGB_F32, collect_stats=1), self.tiles.data_ptr(), stream=stream, stats=True)
@@ -505,7 +506,7 @@ def main():
                     "call": "ftb_render" if world == 1 else (("%d bands: ftb_render_tiles_device (tiles stored into rank 0's memory over NVLink) + barrier + ftb_assemble_rows_device + ftb_host_copy_begin/finish" % bands) if arena
                                                            else "ftb_render_tiles_device + NCCL gather + ftb_assemble_device + ftb_host_copy_begin/finish"),
                     "f64": {"value": rays_per_frame * f64_steps / e2e_f64_s / 1e6, "ms_per_step": 1e3 * e2e_f64_s / f64_steps, "d2h_bytes_per_step": int(W * H * 24), "steps": f64_steps},
-                    "scene_create_ms": run.create_ms},
+                    "scene_create_ms": run.create_ms, "mesh_index": run.build},
             "gpu_launches": int(args.steps * 2),
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "traffic": _traffic_per_launch(args.workload) if world == 1 else None,
@@ -565,7 +566,7 @@ def main():
             e2e_ms = 1e3 * (time.perf_counter() - t0) / k
             ent = {"width": r.W, "height": r.H, "spp": r.spp, "ms_per_step": tot / k, "kernel_ms": kern / k, "value": rays / (tot / k * 1e-3) / 1e6,
                    "e2e_ms_per_step": e2e_ms, "e2e_value": rays / (e2e_ms * 1e-3) / 1e6, "rays_per_frame": rays,
-                   "roofline_frac": r.local_flops / (kern / k * 1e-3) / 1e12 / peak, "scene_create_ms": r.create_ms, "steps": k}
+                   "roofline_frac": r.local_flops / (kern / k * 1e-3) / 1e12 / peak, "scene_create_ms": r.create_ms, "mesh_index": r.build, "steps": k}
             if not args.no_cpu_baseline:
                 res, windows, margin, crays, cores, what = cpu_sample(r.parsed, r.jit, MINI_SAMPLE_PRIMARY, debug=True)
                 ent["cpu_value"] = crays / res["seconds"] / 1e6

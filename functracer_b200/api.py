@@ -63,6 +63,8 @@ def lib():
         L.ftb_host_copy_finish.restype = C.c_int
         L.ftb_check_overflow.argtypes = [vp, vp]
         L.ftb_check_overflow.restype = C.c_int
+        L.ftb_scene_build_info.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.ftb_scene_build_info.restype = C.c_int
         if L.ftb_abi_version() != abi.ABI_VERSION:
             raise RuntimeError("ABI version mismatch: library %d, bindings %d" % (L.ftb_abi_version(), abi.ABI_VERSION))
         _LIB = L
@@ -181,6 +183,12 @@ class Scene:
         _check(lib().ftb_render_tiles_device(self._h, cam, C.byref(p), C.c_void_p(d_tiles_ptr), C.byref(dbg) if dbg is not None else None,
                                              C.byref(st) if st is not None else None, C.c_void_p(stream)))
         return st
+
+    def build_info(self):
+        """dict(bvh_on_device, bvh_build_ms, bvh_total_ms): how the scene's mesh index was built at create time."""
+        on, b, t = C.c_int32(), C.c_double(), C.c_double()
+        _check(lib().ftb_scene_build_info(self._h, C.byref(on), C.byref(b), C.byref(t)))
+        return dict(bvh_on_device=bool(on.value), bvh_build_ms=b.value, bvh_total_ms=t.value)
 
     def check_overflow(self, stream=0):
         """Waits for `stream`; raises FtbError(ERR_HIT_OVERFLOW) if a frame rendered through the device entry points on the

@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "../../../include/functracer_b200.h"
+#include "bvh_build.h"
 #include "device_scene.h"
 #include "lower.h"
 
@@ -285,6 +286,8 @@ struct ftb_scene {
     struct Img { int w, h; std::vector<uint8_t> rgb; };
     std::vector<Img> images;
     std::map<int, std::unique_ptr<PerDevice>> devices;
+    ftb::DeviceBuildStats bvh_stats;  // mesh index built on the device at create time (bvh_build.h)
+    bool bvh_on_device = false;
 };
 
 namespace {
@@ -305,6 +308,12 @@ int upload(std::vector<void*>& allocs, const std::vector<T>& host, const T*& dev
     dev = static_cast<const T*>(p);
     return FTB_OK;
 }
+
+// Meshes of this many (clipped) triangles or more are walked by the whole warp (render.cuh packetMesh) and their samples are
+// dealt one at a time; smaller ones by each lane for itself.  Measured on 960 / 9.6 k / 355 k triangles at 3840x2160x16: private
+// walks 2.92 / 3.41 / 9.11 ms, packet walks 3.19 / 3.60 / 6.38 ms.
+constexpr size_t kLargeMesh = 32768;
+inline bool largeMesh(const Lowered& L) { return L.bvh_tri.size() >= kLargeMesh; }
 
 template <typename R>
 int uploadScene(const ftb_scene& sc, SceneStorage<R>& st)
@@ -350,7 +359,11 @@ int uploadScene(const ftb_scene& sc, SceneStorage<R>& st)
         std::vector<unsigned> casts((L.items.size() + 31) / 32 + 1, 0u);
         for (size_t i = 0; i < L.items.size(); ++i)
             if (L.items[i].casts_shadow) casts[i >> 5] |= 1u << (i & 31);
-        UP(items, v.items) UP(bounds, v.item_bound) UP(ops, v.ops) UP(casts, v.item_casts) UP(progs, v.item_prog)
+        std::vector<unsigned> meshes(casts.size(), 0u);
+        for (size_t i = 0; i < L.items.size(); ++i)
+            if (L.items[i].kind == ITEM_LEAF && L.leaves[(size_t)L.items[i].a].kind == LEAF_MESH) meshes[i >> 5] |= 1u << (i & 31);
+        UP(items, v.items) UP(bounds, v.item_bound) UP(ops, v.ops) UP(casts, v.item_casts) UP(meshes, v.item_mesh) UP(progs, v.item_prog)
+        v.mesh_packet = largeMesh(L) ? 1 : 0;
         v.n_items = (int)L.items.size();
     }
     {
@@ -724,10 +737,11 @@ int launchFrame(ftb_scene* sc, PerDevice* pd, const ftb_camera* cam, const ftb_r
                 F.s_count = std::min(UnitCap<R>::value, g.spp - s_base);
                 // run length: cheap samples amortise the dealing over up to 8 consecutive samples of a pixel, as long as
                 // every pixel still splits into >= 8 runs (the chain a lane can be stuck with stays 1/8 of a pixel)
-                // Mesh scenes deal single samples: a traversal's cost varies so much between neighbouring samples that a lane
-                // stuck with a run of them holds its warp back (measured -14 % on the full-size mesh; moon +7 % the other way).
+                // Large meshes deal single samples: a traversal's cost varies so much between neighbouring samples that a lane
+                // stuck with a run of them holds its warp back (measured -11..-14 % on the 355 k mesh; +3 % on the 960-triangle
+                // one and +7 % on moon the other way).
                 static const int runEnv = [] { const char* e = std::getenv("FTB_RUN_MAX"); int v = e ? std::atoi(e) : 0; return v > 8 ? 8 : v; }();  // A/B switch
-                const int runMax = runEnv > 0 ? runEnv : (sc->L.has_mesh ? 1 : 8);
+                const int runMax = runEnv > 0 ? runEnv : (largeMesh(sc->L) ? 1 : 8);
                 int run = 1;
                 while (run < runMax && F.s_count % (run * 2) == 0 && F.s_count / (run * 2) >= 8) run *= 2;
                 F.run = run;
@@ -829,10 +843,15 @@ int ftb_scene_create(const ftb_scene_desc* desc, ftb_scene** out)
     *out = nullptr;
     std::unique_ptr<ftb_scene> sc(new ftb_scene);
     std::string err;
-    int rc = ftb::lower_scene(*desc, sc->L, err);
+    const auto tc0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        static const bool verbose = std::getenv("FTB_VERBOSE") != nullptr;
+        if (verbose) std::fprintf(stderr, "functracer_b200: scene_create %-14s at %8.2f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tc0).count());
+    };
+    int rc = ftb::lower_scene(*desc, sc->L, err, false);  // the mesh index is built below, on the device
+    lap("lowered");
     if (rc != FTB_OK) return fail(rc, err);
     if (sc->L.max_csg_lists > ftb::kMaxLists) return fail(FTB_ERR_UNSUPPORTED, "CSG nesting needs more than 12 pending hit lists");
-    if (sc->L.max_bvh_depth + 2 > ftb::kBspStack) return fail(FTB_ERR_UNSUPPORTED, "mesh index deeper than the 64-entry traversal stack");
     if (sc->L.leaves.size() >= (1u << 22)) return fail(FTB_ERR_UNSUPPORTED, "more than 4M leaves");
     sc->bsp_nodes.assign(desc->bsp_nodes, desc->bsp_nodes + desc->n_bsp_nodes);
     sc->bsp_leaves.assign(desc->bsp_leaves, desc->bsp_leaves + desc->n_bsp_leaves);
@@ -846,16 +865,47 @@ int ftb_scene_create(const ftb_scene_desc* desc, ftb_scene** out)
         else { im.w = im.h = 1; im.rgb.assign(3, 0); }
         sc->images.push_back(std::move(im));
     }
+    lap("copied");
     // upload to the current device now, so that create fails loudly without a GPU
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n < 1) { (void)cudaGetLastError(); return fail(FTB_ERR_NO_DEVICE, "no CUDA device: functracer_b200 has no CPU path"); }
     int dev = 0;
     CK(cudaGetDevice(&dev));
+    if (sc->L.has_mesh) {
+        // BspMesh.fs:30-65 builds the reference's tree; the device's own index over the same triangles is built here: on the
+        // GPU for large meshes (bvh_build.cu), on the host for small ones (and as fallback / A/B arm: FTB_HOST_BVH=1)
+        static const bool hostBvh = std::getenv("FTB_HOST_BVH") != nullptr;
+        static const bool deviceBvh = std::getenv("FTB_DEVICE_BVH") != nullptr;  // A/B: the device build also for small meshes
+        static const int radiusEnv = [] { const char* e = std::getenv("FTB_PLOC_RADIUS"); return e ? std::atoi(e) : 0; }();
+        std::vector<std::vector<int32_t>> order;
+        ftb::enumerateMeshes(*desc, sc->L, order);
+        size_t meshTriangles = 0;
+        for (const auto& o : order) meshTriangles += o.size();
+        bool done = false;
+        if (!hostBvh && (deviceBvh || meshTriangles >= kLargeMesh)) {
+            const int radii[3] = {radiusEnv > 0 ? radiusEnv : 16, 8, 4};
+            for (int k = 0; k < 3 && !done; ++k) {
+                std::string why;
+                done = ftb::buildMeshIndexDevice(desc->triangles, desc->n_triangles, order, ftb::kBspStack, radii[k], sc->L, sc->bvh_stats, why);
+                if (!done && std::getenv("FTB_VERBOSE")) std::fprintf(stderr, "functracer_b200: device BVH build not used (%s)\n", why.c_str());
+            }
+            sc->bvh_on_device = done;
+        }
+        if (!done) {
+            const auto t0 = std::chrono::steady_clock::now();
+            ftb::buildMeshIndexHost(*desc, sc->L);
+            sc->bvh_stats.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        }
+        if (sc->L.max_bvh_depth + 2 > ftb::kBspStack) return fail(FTB_ERR_UNSUPPORTED, "mesh index deeper than the 64-entry traversal stack");
+        if (largeMesh(sc->L)) sc->L.features |= (unsigned)FT_MESHPK;  // the warp-packet walk (render.cuh)
+    }
+    lap("mesh index");
     PerDevice* pd = nullptr;
     rc = getDevice(sc.get(), dev, &pd);
     if (rc != FTB_OK) return rc;
     rc = uploadScene<float>(*sc, pd->f32);
     if (rc != FTB_OK) return rc;
+    lap("uploaded");
     *out = sc.release();
     return FTB_OK;
 }
@@ -865,6 +915,15 @@ void ftb_scene_destroy(ftb_scene* sc)
     if (!sc) return;
     DeviceRestore restore;
     delete sc;  // ~PerDevice synchronises and releases every device's buffers, streams and events
+}
+
+int ftb_scene_build_info(const ftb_scene* scene, int32_t* bvh_on_device, double* bvh_build_ms, double* bvh_total_ms)
+{
+    if (!scene) return fail(FTB_ERR_BAD_ARG, "null argument");
+    if (bvh_on_device) *bvh_on_device = scene->bvh_on_device ? 1 : 0;
+    if (bvh_build_ms) *bvh_build_ms = scene->bvh_stats.build_ms;
+    if (bvh_total_ms) *bvh_total_ms = scene->bvh_stats.total_ms;
+    return FTB_OK;
 }
 
 int64_t ftb_tile_buffer_bytes(const ftb_render_params* params)

@@ -45,7 +45,9 @@ enum Feature : unsigned {
     FT_TABLE = 0x200,  // enough top-level items for the common-origin bound table to pay (lower.h kFeatOriginTable, render.cuh)
     FT_PAIRG = 0x400,  // CSG pairs (FT_CSG) walk both operands through ONE copy of the leaf intersectors: scenes with many leaf kinds
                        // (instruction footprint) and pairs whose operand is a run of leaves (lower.cpp, render.cuh csgPair)
-    FT_ALL = 0x7ff
+    FT_MESHPK = 0x800,  // a LARGE mesh: mesh leaves are walked by the whole warp (render.cuh packetMesh) instead of by each lane (intersectMesh);
+                        // variants with FT_MESH but without this bit only contain the per-lane walk, FT_ALL contains both (DevScene::mesh_packet)
+    FT_ALL = 0xfff
 };
 
 enum StatSlot : int {
@@ -76,6 +78,8 @@ struct DevScene {
     const int2* item_prog; // CSG items: x = first op, y = op count of the general program
     const R4* item_bound;  // xyz = centre, w = (inflated radius)^2 of a conservative bounding sphere (< 0 unbounded)
     const unsigned* item_casts;  // bit j of word w: item 32 w + j can block light (something under it has applyLighting)
+    const unsigned* item_mesh;   // bit j of word w: item 32 w + j is a mesh leaf
+    int mesh_packet;             // 1: mesh leaves are walked by the whole warp (render.cuh packetMesh; large meshes), 0: by each lane (intersectMesh)
     int n_items;
     const int2* ops;  // CSG programs: x = kind, y = arg
     // surfaces

@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstring>
 #include <map>
+#include <utility>
 
 namespace ftb {
 namespace {
@@ -212,18 +213,48 @@ struct Lowerer {
         int b = bspDepth(d.bsp_nodes[link].left, depth + 1);
         return std::max(a, b);
     }
-    void bspPoints(int link, std::vector<std::array<double, 3>>& pts)
+    void bspRanges(int link, std::vector<std::pair<int, int>>& ranges)
     {
         if (link < 0) {
             const ftb_bsp_leaf& lf = d.bsp_leaves[~link];
-            for (int i = 0; i < lf.tri_count; ++i) {
-                const double* t = d.triangles + 9 * (size_t)(lf.tri_first + i);
-                for (int k = 0; k < 3; ++k) pts.push_back({t[3 * k], t[3 * k + 1], t[3 * k + 2]});
-            }
+            if (lf.tri_count > 0) ranges.push_back({lf.tri_first, lf.tri_count});
             return;
         }
-        bspPoints(d.bsp_nodes[link].right, pts);
-        bspPoints(d.bsp_nodes[link].left, pts);
+        bspRanges(d.bsp_nodes[link].right, ranges);
+        bspRanges(d.bsp_nodes[link].left, ranges);
+    }
+    // Bounding sphere of a mesh's vertices in world space (centre of their box, farthest vertex), straight off the triangle
+    // table: two passes, nothing stored (a 355 k-triangle mesh has a million vertices).
+    Sphere boundOfMesh(const M34& w2m, int root)
+    {
+        M34 m2w;
+        if (!invertAffine(w2m, m2w)) return kUnbounded;
+        std::vector<std::pair<int, int>> ranges;
+        bspRanges(root, ranges);
+        if (ranges.empty()) return kEmpty;
+        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+        auto world = [&](const double* p, double* w) {
+            for (int r = 0; r < 3; ++r) w[r] = m2w.m[4 * r] * p[0] + m2w.m[4 * r + 1] * p[1] + m2w.m[4 * r + 2] * p[2] + m2w.m[4 * r + 3];
+        };
+        for (auto& rg : ranges)
+            for (int i = 0; i < 3 * rg.second; ++i) {
+                double w[3];
+                world(d.triangles + 9 * (size_t)rg.first + 3 * (size_t)i, w);
+                for (int r = 0; r < 3; ++r) { lo[r] = std::min(lo[r], w[r]); hi[r] = std::max(hi[r], w[r]); }
+            }
+        Sphere s;
+        for (int r = 0; r < 3; ++r) s.c[r] = 0.5 * (lo[r] + hi[r]);
+        double r2 = 0;
+        for (auto& rg : ranges)
+            for (int i = 0; i < 3 * rg.second; ++i) {
+                double w[3];
+                world(d.triangles + 9 * (size_t)rg.first + 3 * (size_t)i, w);
+                const double dx = w[0] - s.c[0], dy = w[1] - s.c[1], dz = w[2] - s.c[2];
+                r2 = std::max(r2, dx * dx + dy * dy + dz * dz);
+            }
+        s.r = std::sqrt(r2);
+        if (!std::isfinite(s.r) || !std::isfinite(s.c[0]) || !std::isfinite(s.c[1]) || !std::isfinite(s.c[2])) return kUnbounded;
+        return s;
     }
 
     int addLeaf(int kind, const Ctx& cx, const M34& w2m, int surface, int prim, int payload, const std::vector<std::array<double, 3>>& modelPts, bool bounded)
@@ -273,9 +304,8 @@ struct Lowerer {
             L.max_bsp_depth = std::max(L.max_bsp_depth, depth);
             if (L.mesh_used.size() < (size_t)d.n_meshes) L.mesh_used.resize((size_t)d.n_meshes, 0);
             L.mesh_used[n.b] = 1;
-            std::vector<std::array<double, 3>> pts;
-            bspPoints(d.meshes[n.b].root, pts);
-            out.push_back(addLeaf(LEAF_MESH, cx, cx.w2m, surface, prim, n.b, pts, true));
+            out.push_back(addLeaf(LEAF_MESH, cx, cx.w2m, surface, prim, n.b, {}, false));
+            leafBound.back() = boundOfMesh(cx.w2m, d.meshes[n.b].root);
             L.has_mesh = true;
             break;
         }
@@ -584,10 +614,11 @@ void enumerateBsp(const ftb_scene_desc& d, int link, std::vector<int32_t>& out, 
 
 void buildMeshIndex(const ftb_scene_desc& d, Lowered& L)
 {
+    std::vector<std::vector<int32_t>> order;
+    enumerateMeshes(d, L, order);
     L.mesh_root.assign((size_t)std::max(0, d.n_meshes), ~0);
     for (int m = 0; m < d.n_meshes; ++m) {
-        std::vector<int32_t> tri;
-        if ((size_t)m < L.mesh_used.size() && L.mesh_used[m]) enumerateBsp(d, d.meshes[m].root, tri, 0);
+        const std::vector<int32_t>& tri = order[(size_t)m];
         BvhBuilder bb(d.triangles, L);
         bb.slotBase = (int)L.bvh_tri.size();
         bb.ref = tri;
@@ -609,7 +640,16 @@ void buildMeshIndex(const ftb_scene_desc& d, Lowered& L)
 
 }  // namespace
 
-int lower_scene(const ftb_scene_desc& d, Lowered& out, std::string& err)
+void enumerateMeshes(const ftb_scene_desc& d, const Lowered& L, std::vector<std::vector<int32_t>>& order)
+{
+    order.assign((size_t)std::max(0, d.n_meshes), std::vector<int32_t>());
+    for (int m = 0; m < d.n_meshes; ++m)
+        if ((size_t)m < L.mesh_used.size() && L.mesh_used[m]) enumerateBsp(d, d.meshes[m].root, order[(size_t)m], 0);
+}
+
+void buildMeshIndexHost(const ftb_scene_desc& d, Lowered& L) { buildMeshIndex(d, L); }
+
+int lower_scene(const ftb_scene_desc& d, Lowered& out, std::string& err, bool build_mesh_index)
 {
     if (!d.nodes || d.n_nodes <= 0) { err = "scene has no nodes"; return FTB_ERR_BAD_SCENE; }
     if ((d.n_children > 0 && !d.children) || (d.n_transforms > 0 && !d.transforms) || (d.n_materials > 0 && !d.materials) ||
@@ -663,7 +703,7 @@ int lower_scene(const ftb_scene_desc& d, Lowered& out, std::string& err)
         if (lf.top_level && (lf.kind == LEAF_PLANE || lf.kind == LEAF_SQUARE || lf.kind == LEAF_CIRCLE)) f |= 0x100;
     if (wantsOriginTable((int)out.items.size(), d.n_lights)) f |= kFeatOriginTable;
     out.features = f;
-    if (out.has_mesh) buildMeshIndex(d, out);
+    if (out.has_mesh && build_mesh_index) buildMeshIndex(d, out);
     return FTB_OK;
 }
 

@@ -140,12 +140,19 @@ struct Lowered {
     bool has_csg = false, has_mesh = false, has_texture = false, has_image = false;
     bool has_soft_light = false, has_rough = false, has_reflection = false;
     // Kernel features this scene needs, as device_scene.h `Feature` bits (cube 1, round 2, mesh 4, csg 8,
-    // texture 16, Oren-Nayar 32, rng 64, general CSG 128, top-level planar leaf 256, bound table 512, pair with a run operand 1024);
+    // texture 16, Oren-Nayar 32, rng 64, general CSG 128, top-level planar leaf 256, bound table 512, shared-copy pairs 1024; api.cu adds 2048 for a large mesh);
     // camera depth of field adds rng at render time.
     unsigned features = 0;
 };
 
-// Returns FTB_OK or a negative ftb_status with a message in err.
-int lower_scene(const ftb_scene_desc& d, Lowered& out, std::string& err);
+// Returns FTB_OK or a negative ftb_status with a message in err.  build_mesh_index = false leaves the mesh index
+// (bvh_nodes, bvh_tri, bvh_seq, mesh_root) to the caller: the device build of bvh_build.h, or buildMeshIndexHost.
+int lower_scene(const ftb_scene_desc& d, Lowered& out, std::string& err, bool build_mesh_index = true);
+
+// order[m] = the triangles of mesh m in BspMesh.intersect's enumeration order (right subtree before left,
+// BspMesh.fs:72-75); empty for meshes no bspMesh primitive uses.
+void enumerateMeshes(const ftb_scene_desc& d, const Lowered& L, std::vector<std::vector<int32_t>>& order);
+// The host build of the mesh index (binned SAH), the fallback of the device build.
+void buildMeshIndexHost(const ftb_scene_desc& d, Lowered& L);
 
 }  // namespace ftb

@@ -267,6 +267,11 @@ const char* ftb_last_error(void);
 int ftb_scene_create(const ftb_scene_desc* desc, ftb_scene** out);
 void ftb_scene_destroy(ftb_scene* scene);
 
+/* How the mesh index of the scene was built (BspMesh.fs:30-65 is the reference's own, lazily clipped tree; the
+ * device traverses its own index over the same triangles, built on the GPU at create time): whether the device
+ * build was used, the device time of its kernels and the wall time including transfers (0 without meshes). */
+int ftb_scene_build_info(const ftb_scene* scene, int32_t* bvh_on_device, double* bvh_build_ms, double* bvh_total_ms);
+
 /* Host-buffer entry point = the drop-in for Program.fs:54-64.  out is caller-allocated:
  * W*H pixels in params->out_format, row-major (y, then x), blended (Image.fs:112-116 /
  * 134-144) and un-clamped unless RGBA8.  dbg and stats may be NULL.

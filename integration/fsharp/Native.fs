@@ -141,6 +141,8 @@ type FtbRenderParams =
     val mutable shardCount: int
     val mutable nGpus: int
     val mutable collectStats: int
+    val mutable bandIndex: int       // ftb_render_tiles_device only (ABI 4): one band of tile rows of the shard; 0 / 0 = all
+    val mutable bandCount: int
     val mutable reserved: int
 
 [<Literal>]
