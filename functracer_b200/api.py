@@ -63,8 +63,11 @@ def lib():
         L.ftb_host_copy_finish.restype = C.c_int
         L.ftb_check_overflow.argtypes = [vp, vp]
         L.ftb_check_overflow.restype = C.c_int
-        L.ftb_scene_build_info.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_double)]
-        L.ftb_scene_build_info.restype = C.c_int
+        if os.environ.get("FTB_LIB") and not hasattr(L, "ftb_scene_build_info"):
+            L.ftb_scene_build_info = None  # an older A/B build of the same ABI (tools/ab_build.sh REV)
+        else:
+            L.ftb_scene_build_info.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+            L.ftb_scene_build_info.restype = C.c_int
         if L.ftb_abi_version() != abi.ABI_VERSION:
             raise RuntimeError("ABI version mismatch: library %d, bindings %d" % (L.ftb_abi_version(), abi.ABI_VERSION))
         _LIB = L
@@ -187,6 +190,8 @@ class Scene:
     def build_info(self):
         """dict(bvh_on_device, bvh_build_ms, bvh_total_ms): how the scene's mesh index was built at create time."""
         on, b, t = C.c_int32(), C.c_double(), C.c_double()
+        if lib().ftb_scene_build_info is None:
+            return dict(bvh_on_device=False, bvh_build_ms=0.0, bvh_total_ms=0.0)
         _check(lib().ftb_scene_build_info(self._h, C.byref(on), C.byref(b), C.byref(t)))
         return dict(bvh_on_device=bool(on.value), bvh_build_ms=b.value, bvh_total_ms=t.value)
 

@@ -1436,7 +1436,8 @@ __global__ void __launch_bounds__(kBlockThreads, MinBlocks<FEAT>::value) render_
             const bool mine = phase == PH_NEAREST ? (fastPrimary && limit == F.recursion_limit) : tmax < realmax_<R>();  // finite tmax: a point light
             tabled = !__any_sync(full, phase != PH_IDLE && !hold && !mine);
         }
-        const unsigned tracing = __ballot_sync(full, !(phase == PH_IDLE || hold));  // the lanes that trace a ray in this iteration
+        unsigned tracing = full;  // variants with the packet walk: the lanes that trace a ray in this iteration
+        if constexpr (MeshWalks<FEAT>::kPacket) tracing = __ballot_sync(full, !(phase == PH_IDLE || hold));
         if (phase == PH_IDLE || hold) continue;
 
         // ---- trace this lane's current ray: the one expensive step ------------------------------------------------
