@@ -99,12 +99,12 @@ FTB_FEAT_LIST_F32
 FTB_FEAT_LIST_F64
 #undef X
 static const Variant<float> kVariantsF32[] = {
-#define X(feat) {(unsigned)(feat), (feat) == FT_ALL, launch_f32_##feat},
+#define X(feat) {(unsigned)(feat), UnitCap<float, (unsigned)(feat)>::value, (feat) == FT_ALL, launch_f32_##feat},
     FTB_FEAT_LIST_F32
 #undef X
 };
 static const Variant<double> kVariantsF64[] = {
-#define X(feat) {(unsigned)(feat), (feat) == FT_ALL, launch_f64_##feat},
+#define X(feat) {(unsigned)(feat), UnitCap<double, (unsigned)(feat)>::value, (feat) == FT_ALL, launch_f64_##feat},
     FTB_FEAT_LIST_F64
 #undef X
 };
@@ -732,9 +732,9 @@ int launchFrame(ftb_scene* sc, PerDevice* pd, const ftb_camera* cam, const ftb_r
             F.bw_log = bw == 8 ? 3 : (bw == 4 ? 2 : (bw == 2 ? 1 : 0));
             F.bh_log = bh == 4 ? 2 : (bh == 2 ? 1 : 0);
             F.n_blocks = ntile * (FTB_TILE_PIXELS / ppb);
-            for (int s_base = 0; s_base < g.spp; s_base += UnitCap<R>::value) {
+            for (int s_base = 0; s_base < g.spp; s_base += var->unit_cap) {
                 F.s_base = s_base;
-                F.s_count = std::min(UnitCap<R>::value, g.spp - s_base);
+                F.s_count = std::min(var->unit_cap, g.spp - s_base);
                 // run length: cheap samples amortise the dealing over up to 8 consecutive samples of a pixel, as long as
                 // every pixel still splits into >= 8 runs (the chain a lane can be stuck with stays 1/8 of a pixel)
                 // Large meshes deal single samples: a traversal's cost varies so much between neighbouring samples that a lane

@@ -12,12 +12,19 @@ constexpr int kHitCap = 32;    // per-ray CSG hit stack entries
 constexpr int kMaxLists = 12;  // per-ray CSG list stack depth
 constexpr int kBspStack = 64;  // per-ray mesh traversal stack
 constexpr int kBlockThreads = 128;
-// most samples of one unit of the blend ring (render.cuh): a launch covers at most this many samples per pixel,
-// frames with more are rendered in several passes that continue the same left fold
-#ifndef FTB_UNIT_CAP
-#define FTB_UNIT_CAP 128
+// Most samples of one unit of the blend ring (render.cuh): a launch covers at most this many samples per pixel, frames with
+// more are rendered in several passes that continue the same left fold.  128 (FP32) / 64 (FP64) in general; 256 for the variants
+// of simple scenes (spheres / planes only: no cube, round leaf, mesh or CSG), whose samples are cheap: at 64 spp a 128-sample unit
+// is two pixels and its fold keeps 6 of 32 lanes busy (moon, 64 spp: -7.7 % with 256; the house family: +10 %, the larger ring
+// takes shared memory away from the L1 those scenes need - hence per variant).
+constexpr unsigned kHeavyFeatures = 0x01u | 0x02u | 0x04u | 0x08u | 0x80u;  // FT_CUBE | FT_ROUND | FT_MESH | FT_CSG | FT_CSGN
+template <typename R, unsigned FEAT> struct UnitCap {
+#ifdef FTB_UNIT_CAP
+    static constexpr int value = sizeof(R) == 4 ? FTB_UNIT_CAP : 64;
+#else
+    static constexpr int value = sizeof(R) == 4 ? ((FEAT & kHeavyFeatures) == 0 ? 256 : 128) : 64;
 #endif
-template <typename R> struct UnitCap { static constexpr int value = sizeof(R) == 4 ? FTB_UNIT_CAP : 64; };
+};
 
 template <typename R>
 struct V4;
@@ -147,6 +154,7 @@ struct DevFrame {
 template <typename R>
 struct Variant {
     unsigned feat;
+    int unit_cap;    // UnitCap<R, feat>: samples per pixel one launch covers
     bool has_stats;  // the counting kernel is only compiled into the FT_ALL variants
     cudaError_t (*launch)(const DevScene<R>& s, const DevFrame<R>& f, bool stats, int sm_count, cudaStream_t stream, int* launches);
 };

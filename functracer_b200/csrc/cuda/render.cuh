@@ -1187,13 +1187,17 @@ FTB_DEV Ray<R> primaryRay(const DevFrame<R>& F, int px, int py, int s, unsigned 
 }
 
 // ---- the kernel ------------------------------------------------------------------------------------------------------
-// Resident CTAs per SM.  5 (<= 102 registers, 20 warps / SM) measured 3-7 % faster than 4 on cfg2 / cfg3 and faster than
-// 6 / 8 everywhere except on the mesh-only variant, whose traversal waits on dependent node fetches: 6 CTAs there
-// (-3 % bundled mesh, -6 % full-size mesh; 8 is slower again).  The FP64 verification build passes -DFTB_MIN_BLOCKS=1.
+// Resident CTAs per SM, per variant (measured, profiles/r2a_*, r2m_*): 5 (<= 102 registers, 20 warps / SM) in general - 3-7 %
+// faster than 4 on cfg2 and the simple scenes (moon +10 % at 4), faster than 6 / 8; 6 for the mesh-only variants, whose walks wait
+// on dependent node fetches; 4 (128 registers) for the variants with the shared-copy pairs or the general CSG evaluator (the
+// house family), which spill 550 bytes at 96 registers: house -11 %, night-house -7 %, repeat -2 % at 4.
+// The FP64 verification build passes -DFTB_MIN_BLOCKS=1.
 #ifdef FTB_MIN_BLOCKS
 template <unsigned FEAT> struct MinBlocks { static constexpr int value = FTB_MIN_BLOCKS; };
 #else
-template <unsigned FEAT> struct MinBlocks { static constexpr int value = (FEAT == (unsigned)FT_MESH || FEAT == (unsigned)(FT_MESH | FT_MESHPK)) ? 6 : 5; };
+template <unsigned FEAT> struct MinBlocks {
+    static constexpr int value = (FEAT == (unsigned)FT_MESH || FEAT == (unsigned)(FT_MESH | FT_MESHPK)) ? 6 : ((FEAT & (FT_PAIRG | FT_CSGN)) != 0 ? 4 : 5);
+};
 #endif
 #ifndef FTB_PHASE_ALIGN
 #define FTB_PHASE_ALIGN 1
@@ -1201,7 +1205,7 @@ template <unsigned FEAT> struct MinBlocks { static constexpr int value = (FEAT =
 enum Phase : int { PH_IDLE = 0, PH_NEAREST = 1, PH_SHADOW = 2, PH_START = 3 };
 
 // Blend ring: every warp keeps up to kRingSlots units in flight; a unit is a run of pixels of one 8x4 block times the
-// samples of this pass (<= UnitCap<R> samples).  Lanes take SAMPLES, not pixels: the longest sequential chain a lane
+// samples of this pass (<= UnitCap<R, FEAT> samples).  Lanes take SAMPLES, not pixels: the longest sequential chain a lane
 // can be stuck with is one sample's bounce chain, not spp of them, which is what bounds the kernel's tail and its
 // strong scaling.  Finished sample colours are parked in the unit's slot in shared memory; when the last sample of a
 // unit lands, the warp folds each pixel's samples IN SAMPLE ORDER (Array.average folds from Zero, Image.fs:112-116),
@@ -1239,7 +1243,7 @@ template <typename R, unsigned FEAT, bool STATS>
 __global__ void __launch_bounds__(kBlockThreads, MinBlocks<FEAT>::value) render_kernel(const __grid_constant__ DevScene<R> S, const __grid_constant__ DevFrame<R> F)
 {
     typedef typename V4<R>::type R4;
-    constexpr int CAP = UnitCap<R>::value;
+    constexpr int CAP = UnitCap<R, FEAT>::value;
     constexpr int WARPS = kBlockThreads / 32;
     __shared__ R ring_col[WARPS][kRingSlots][CAP * 3];
     __shared__ int ring_hdr[WARPS][kRingSlots][4];  // out slot of the block's pixel 0, block width, first pixel, pixel count

@@ -222,6 +222,14 @@ def test_sample_counts_and_multi_pass_blend(spp, prec):
         assert np.abs(got["rgb"] - ref["rgb"]).max() < 1e-9
 
 
+def test_multi_pass_blend_in_a_256_sample_variant():
+    """The variants of simple scenes (spheres / planes only) hold 256 samples per blend unit; 300 samples per pixel take two
+    passes that continue the same left fold."""
+    text = scenes.moon(res=(24, 20), spp=300)
+    ref, got = both(text, precision=abi.PRECISION_FP32, jitter_seed=9)
+    check(ref, got, abi.PRECISION_FP32, "moon-spp300")
+
+
 def test_banded_host_render_matches_device_path():
     """ftb_render overlaps the D2H copy of finished bands of tile rows with the rendering of later bands (frames
     of >= 512x512).  Bands, tile order and queue block size only change WHEN a sample is traced, never its

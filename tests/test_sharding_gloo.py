@@ -1,6 +1,7 @@
-"""The N > 1 plumbing on CPU: two gloo ranks each own the tiles `t % 2 == rank` of a frame, gather their
-tile-major buffers to rank 0 (functracer_b200.dist.gather_tiles) and rank 0 assembles the frame with the
-host twin of ftb_assemble_device.  The per-shard pixels come from the CPU oracle (there is no GPU here);
+"""The N > 1 plumbing on CPU: two gloo ranks each own the tiles `t % 2 == rank` of a frame, "render" them band by band
+(the band geometry comes from the library's own ftb_band_rows / ftb_tile_buffer_bytes, which need no device), gather their
+tile-major buffers to rank 0 (functracer_b200.dist.gather_tiles) and rank 0 assembles the frame with the host twin of
+ftb_assemble_device (tests/tile_twin.py).  The per-shard pixels come from the CPU oracle (there is no GPU here);
 what is under test is the partition / layout / gather contract of the C ABI."""
 import os
 import socket
@@ -11,7 +12,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from functracer_b200 import abi, api, frontend, scenes, tiles
+import tile_twin as tiles
+from functracer_b200 import abi, api, frontend, scenes
 from oracle import ftb_oracle as orc
 
 W, H, SPP = 70, 37, 2  # deliberately not multiples of the 16 x 16 tile
@@ -39,6 +41,19 @@ def _worker(rank, world, port, q):
         from functracer_b200 import dist as fdist
         frame = _frame()  # every rank "renders" with the oracle and keeps only its own tiles
         mine = tiles.pack(frame, rank, world)
+        # ... band by band, as bench.py's multi-process e2e path does: the bands of the library partition this shard's tiles
+        bands = 3
+        pb = api.make_params(W, H, SPP, [0.0] * (2 * SPP), shard_index=rank, shard_count=world)
+        rows = [api.band_rows(pb, c, bands) for c in range(bands)]
+        assert rows[0][0] == 0 and rows[-1][1] == H and all(a[1] == b[0] for a, b in zip(rows, rows[1:]))
+        banded = np.zeros_like(mine)
+        mine_tiles = tiles.local_tiles(W, H, rank, world)
+        n = abi.TILE_PIXELS * 3
+        for c in range(bands):
+            for k, t in enumerate(mine_tiles):
+                if tiles.band_of_tile(t, W, H, bands, rows) == c:
+                    banded[k * n:(k + 1) * n] = mine[k * n:(k + 1) * n]
+        assert (banded == mine).all()
         # the C ABI agrees on the buffer size of this shard (argument-only call: no device needed)
         p = api.make_params(W, H, SPP, [0.0] * (2 * SPP), shard_index=rank, shard_count=world, precision=abi.PRECISION_FP64_VERIFY)
         assert api.tile_buffer_bytes(p) == mine.size * 8

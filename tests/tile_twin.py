@@ -1,6 +1,7 @@
-"""Tile sharding contract of the C ABI (include/functracer_b200.h: FTB_TILE_W/H, shard_index/shard_count),
-restated on the host for the multi-process plumbing: which tiles a shard owns, how its tile-major buffer
-is laid out, and how N shard buffers become the row-major frame (what ftb_assemble_device does on the GPU).
+"""TEST INFRASTRUCTURE (not part of the product package): the tile sharding contract of the C ABI
+(include/functracer_b200.h: FTB_TILE_W/H, shard_index/shard_count) restated on the host for the CPU tests of the
+multi-process plumbing: which tiles a shard owns, how its tile-major buffer is laid out, and how N shard buffers
+become the row-major frame (what ftb_assemble_device does on the GPU).
 
 Pixels are independent in the reference (Shading.fs:141-147 shades 1000-ray chunks independently), so any
 partition is legal; this one is 16x16 tiles dealt round-robin: tile t belongs to shard t % N and is that
@@ -8,7 +9,7 @@ shard's local tile t // N.
 """
 import numpy as np
 
-from . import abi
+from functracer_b200 import abi
 
 
 def grid(width, height):
@@ -53,3 +54,14 @@ def assemble(buffers, width, height):
         h, w = min(abi.TILE_H, height - y0), min(abi.TILE_W, width - x0)
         out[y0:y0 + h, x0:x0 + w] = blk[:h, :w]
     return out
+
+
+def band_of_tile(t, width, height, band_count, rows_of_band):
+    """The band (ftb_band_rows) a global tile belongs to: bands are whole tile rows."""
+    tx, _ = grid(width, height)
+    y0 = (t // tx) * abi.TILE_H
+    for c in range(band_count):
+        a, b = rows_of_band[c]
+        if a <= y0 < b:
+            return c
+    raise ValueError("tile row outside every band")

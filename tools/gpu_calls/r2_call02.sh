@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round 2, GPU call 2: the whole GPU suite on the adopted build, the new bench line, mesh run-length A/B, ncu evidence.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 rm -f gpurun_out/fullsize_parity.jsonl
 timeout 1500 python -m pytest tests -m gpu -q -rf 2>&1 | tail -150 > gpurun_out/r2b_gputests.log
 tail -5 gpurun_out/r2b_gputests.log

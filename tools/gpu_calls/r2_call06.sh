@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round 2, GPU call 6: packet traversal with the cull on pop; mesh index built on the device (PLOC) against the host SAH build; GPU suite.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 export FTB_VERBOSE=1
 echo "== host-built index (FTB_HOST_BVH=1): per-lane walk (bvh2) vs packet walk (tree)"
 FTB_HOST_BVH=1 bash tools/ab_bench.sh "cfg4-bunny cfg4-bunny-d12 cfg4-bunny-full-d14" "bvh2 tree" 2>&1 | tee gpurun_out/r2f_packet_hostbvh.log

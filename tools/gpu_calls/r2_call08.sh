@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round 2, GPU call 8: large-mesh variant 0x804 / small-mesh variant 0x004, PLOC radius 40, stream-ordered build buffers; create phases; GPU suite.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 echo "== device-built index (default)"
 bash tools/ab_bench.sh "cfg4-bunny cfg4-bunny-d12 cfg4-bunny-full-d14" "tree" 2>&1 | tee gpurun_out/r2h_mesh_device.log
 echo "== host-built index (FTB_HOST_BVH=1)"

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round 2, GPU call 10 (8 GPUs): the sweep config at 8 and 4 ranks.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 for n in 8 4; do
   timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2951$n bench.py --gpus $n --steps 10 --warmup 3 > gpurun_out/r2j_bench_n$n.json 2> gpurun_out/r2j_bench_n$n.err; echo "n=$n rc=$?"; tail -3 gpurun_out/r2j_bench_n$n.err | cut -c1-300
 done

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round 2, GPU call 11: one-copy leaf intersectors (ab/libftb_onecopy.so) vs the tree on the house family; mesh configs on the final
 # policy (device-built index for large meshes); GPU suite; ncu of the packet walk on the 355 k-triangle mesh.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 bash tools/ab_bench.sh "cfg3-house cfg3-night-house cfg5-repeat" "tree onecopy" 2>&1 | tee gpurun_out/r2k_onecopy_ab.log
 bash tools/ab_bench.sh "cfg4-bunny cfg4-bunny-d12 cfg4-bunny-full-d14" "tree" 2>&1 | tee gpurun_out/r2k_mesh_final.log
 FTB_HOST_BVH=1 bash tools/ab_bench.sh "cfg4-bunny-full-d14" "tree" 2>&1 | tee -a gpurun_out/r2k_mesh_final.log
