@@ -35,7 +35,7 @@ template <typename R>
 __device__ __forceinline__ void loadTilePixel(const TilePtrs& bufs, int shard_count, int tiles_x, int x, int y, R& r, R& g, R& b)
 {
     const int tile = (y / FTB_TILE_H) * tiles_x + (x / FTB_TILE_W);
-    const int shard = tile % shard_count, local = tile / shard_count;
+    const int shard = shardOfTile(tile, shard_count), local = tile / shard_count;
     const R* src = static_cast<const R*>(bufs.p[shard]) + 3 * ((long long)local * FTB_TILE_PIXELS + (y % FTB_TILE_H) * FTB_TILE_W + (x % FTB_TILE_W));
     r = src[0]; g = src[1]; b = src[2];
 }
@@ -92,19 +92,21 @@ __global__ void widen_kernel(const R* in, double* out, long long n)
 namespace ftb {
 static_assert((unsigned)FT_TABLE == kFeatOriginTable, "lower.h and device_scene.h disagree on the table feature bit");
 // kernel variants compiled by the Makefile (render_variant.cu), listed through -DFTB_FEAT_LIST_F32 / _F64
-#define X(feat) cudaError_t launch_f32_##feat(const DevScene<float>&, const DevFrame<float>&, bool, int, cudaStream_t, int*);
+#define X(feat) cudaError_t launch_f32_##feat(const DevScene<float>&, const DevFrame<float>&, bool, int, cudaStream_t, int*); \
+    cudaError_t launch_wf_f32_##feat(const DevScene<float>&, const DevFrame<float>&, int, int, bool, int, void*, size_t, cudaStream_t, int*);
 FTB_FEAT_LIST_F32
 #undef X
-#define X(feat) cudaError_t launch_f64_##feat(const DevScene<double>&, const DevFrame<double>&, bool, int, cudaStream_t, int*);
+#define X(feat) cudaError_t launch_f64_##feat(const DevScene<double>&, const DevFrame<double>&, bool, int, cudaStream_t, int*); \
+    cudaError_t launch_wf_f64_##feat(const DevScene<double>&, const DevFrame<double>&, int, int, bool, int, void*, size_t, cudaStream_t, int*);
 FTB_FEAT_LIST_F64
 #undef X
 static const Variant<float> kVariantsF32[] = {
-#define X(feat) {(unsigned)(feat), UnitCap<float, (unsigned)(feat)>::value, (feat) == FT_ALL, launch_f32_##feat},
+#define X(feat) {(unsigned)(feat), UnitCap<float, (unsigned)(feat)>::value, (feat) == FT_ALL, launch_f32_##feat, launch_wf_f32_##feat},
     FTB_FEAT_LIST_F32
 #undef X
 };
 static const Variant<double> kVariantsF64[] = {
-#define X(feat) {(unsigned)(feat), UnitCap<double, (unsigned)(feat)>::value, (feat) == FT_ALL, launch_f64_##feat},
+#define X(feat) {(unsigned)(feat), UnitCap<double, (unsigned)(feat)>::value, (feat) == FT_ALL, launch_f64_##feat, launch_wf_f64_##feat},
     FTB_FEAT_LIST_F64
 #undef X
 };
@@ -232,7 +234,7 @@ struct PerDevice {
     SceneStorage<double> f64;
     cudaStream_t stream = nullptr;  // owned; used by the host-buffer entry points
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, done = nullptr;
-    DevBuf control, jitter, tiles, out, dbg_prim, dbg_sub, dbg_t, rays, order;
+    DevBuf control, jitter, tiles, out, dbg_prim, dbg_sub, dbg_t, rays, order, wavefront;
     std::vector<int> chunk_first;          // first position in the tile order of every chunk (+ end)
     cudaStream_t copy_stream = nullptr;    // assembly / D2H of finished bands while later bands render (highest priority)
     std::vector<cudaEvent_t> band_events;
@@ -255,7 +257,7 @@ struct PerDevice {
             if (stream) cudaStreamSynchronize(stream);
             if (copy_stream) cudaStreamSynchronize(copy_stream);
             f32.release(); f64.release();
-            for (DevBuf* b : {&control, &jitter, &tiles, &out, &dbg_prim, &dbg_sub, &dbg_t, &rays, &order}) b->release();
+            for (DevBuf* b : {&control, &jitter, &tiles, &out, &dbg_prim, &dbg_sub, &dbg_t, &rays, &order, &wavefront}) b->release();
             for (DevBuf& b : peer_tiles) b.release();
             copier.release();
             if (ev0) cudaEventDestroy(ev0);
@@ -488,7 +490,7 @@ int frameGeom(const ftb_render_params* p, FrameGeom& g)
     g.shard_index = p->shard_count > 1 ? p->shard_index : 0;
     if (g.shard_count > kMaxShards) return fail(FTB_ERR_BAD_ARG, "shard_count exceeds 64");
     if (g.shard_index < 0 || g.shard_index >= g.shard_count) return fail(FTB_ERR_BAD_ARG, "shard_index out of range");
-    g.n_local_tiles = (g.n_tiles - g.shard_index + g.shard_count - 1) / g.shard_count;
+    g.n_local_tiles = (g.n_tiles + g.shard_count - 1) / g.shard_count;  // one per group of shard_count tiles (device_scene.h tileOfLocal); the last group may lack this shard's
     g.n_samples = (long long)g.gw * g.gh * g.spp;
     g.band_count = p->band_count > 1 ? p->band_count : 1;
     g.band_index = p->band_count > 1 ? p->band_index : 0;
@@ -633,14 +635,15 @@ bool computeTileOrder(const ftb_scene& sc, const ftb_camera& c, const ftb_render
         any = true;
     }
     // chunks = bands of tile rows (only used unsharded), see bandFirstRow
-    auto chunkOf = [&](int l) { return n_chunks <= 1 ? 0 : bandOfRow((l * g.shard_count + g.shard_index) / g.tiles_x, n_chunks, g.tiles_y); };
+    auto tileOf = [&](int l) { return tileOfLocal(l, g.shard_index, g.shard_count); };
+    auto chunkOf = [&](int l) { return n_chunks <= 1 ? 0 : bandOfRow(std::min(tileOf(l), g.n_tiles - 1) / g.tiles_x, n_chunks, g.tiles_y); };
     chunk_first.assign((size_t)n_chunks + 1, 0);
     for (int l = 0; l < g.n_local_tiles; ++l) chunk_first[(size_t)chunkOf(l) + 1]++;
     for (int k = 0; k < n_chunks; ++k) chunk_first[(size_t)k + 1] += chunk_first[(size_t)k];
     if (!any && n_chunks <= 1) return false;
     order.resize((size_t)g.n_local_tiles);
     for (int l = 0; l < g.n_local_tiles; ++l) order[l] = l;
-    auto costOf = [&](int l) { return cost[(size_t)l * g.shard_count + g.shard_index]; };
+    auto costOf = [&](int l) { const int t = tileOf(l); return t < g.n_tiles ? cost[(size_t)t] : 0.0f; };
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
         const int ca = chunkOf(a), cb = chunkOf(b);
         return ca != cb ? ca < cb : costOf(a) > costOf(b);
@@ -732,6 +735,21 @@ int launchFrame(ftb_scene* sc, PerDevice* pd, const ftb_camera* cam, const ftb_r
             F.bw_log = bw == 8 ? 3 : (bw == 4 ? 2 : (bw == 2 ? 1 : 0));
             F.bh_log = bh == 4 ? 2 : (bh == 2 ? 1 : 0);
             F.n_blocks = ntile * (FTB_TILE_PIXELS / ppb);
+            // A/B arm (FTB_WAVEFRONT=1): the same frame through the wavefront kernels of wavefront.cuh, where the variant has them
+            static const bool wantWavefront = std::getenv("FTB_WAVEFRONT") != nullptr;
+            if (wantWavefront && !wantStats) {
+                int rph = 0;
+                for (const ftb_light& l : sc->lights) rph += l.kind == FTB_LIGHT_SOFT_DIRECTIONAL ? std::max(l.samples, 0) : 1;
+                rph = std::max(rph, 1);
+                const size_t perPath = 4 * sizeof(typename V4<R>::type) + 3 * sizeof(int) + 3 * sizeof(R) + (size_t)rph * (2 * sizeof(typename V4<R>::type) + 2 * sizeof(int));
+                const size_t want = std::min<size_t>((size_t)ntile * FTB_TILE_PIXELS * (size_t)g.spp * perPath + 65536, (size_t)8 << 30);
+                CK(pd->wavefront.reserve(want));
+                F.s_base = 0; F.s_count = g.spp; F.run = 1; F.rpp_magic = 0;
+                cudaError_t we = var->launch_wavefront(st.view, F, ntile, rph, sc->L.has_reflection, pd->sm_count, pd->wavefront.p, pd->wavefront.cap, stream, &launches);
+                if (we == cudaSuccess) { if (chunkDone) { int rc = (*chunkDone)(chunk); if (rc != FTB_OK) return rc; } continue; }
+                if (we != cudaErrorNotSupported) return cudaFail(we, "wavefront launch");
+                (void)cudaGetLastError();  // this variant has no wavefront arm: the megakernel below
+            }
             for (int s_base = 0; s_base < g.spp; s_base += var->unit_cap) {
                 F.s_base = s_base;
                 F.s_count = std::min(var->unit_cap, g.spp - s_base);

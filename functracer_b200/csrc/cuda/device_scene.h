@@ -26,6 +26,23 @@ template <typename R, unsigned FEAT> struct UnitCap {
 #endif
 };
 
+// Tile -> shard dealing (multi-GPU).  The tiles of a frame are cut into groups of n consecutive tiles (row-major); group g gives
+// one tile to every shard and is every shard's local tile g.  WHICH tile of the group a shard gets is rotated by a hash of g:
+// dealing tile t to shard t % n hands every shard fixed tile COLUMNS whenever the tile row length is a multiple of n (an 8K
+// frame is 480 tiles wide: 8 GPUs would each render vertical stripes, and a scene of upright objects then loads them unevenly).
+__host__ __device__ inline int shardRot(int group, int n) { return n > 1 ? (int)((((unsigned)group * 2654435761u) >> 10) % (unsigned)n) : 0; }
+__host__ __device__ inline int tileOfLocal(int ltile, int shard, int n)  // may be >= the frame's tile count in the last group: no such tile
+{
+    int k = shard - shardRot(ltile, n);
+    if (k < 0) k += n;
+    return ltile * n + k;
+}
+__host__ __device__ inline int shardOfTile(int tile, int n)  // its local index is tile / n
+{
+    const int g = tile / n;
+    return (tile - g * n + shardRot(g, n)) % n;
+}
+
 template <typename R>
 struct V4;
 template <>
@@ -157,6 +174,9 @@ struct Variant {
     int unit_cap;    // UnitCap<R, feat>: samples per pixel one launch covers
     bool has_stats;  // the counting kernel is only compiled into the FT_ALL variants
     cudaError_t (*launch)(const DevScene<R>& s, const DevFrame<R>& f, bool stats, int sm_count, cudaStream_t stream, int* launches);
+    // the wavefront formulation of the same frame (wavefront.cuh), compiled into the variants of the A/B (else null)
+    cudaError_t (*launch_wavefront)(const DevScene<R>& s, const DevFrame<R>& f, int n_tiles, int rays_per_hit, bool reflective, int sm_count, void* scratch, size_t scratch_bytes,
+                                    cudaStream_t stream, int* launches);
 };
 
 }  // namespace ftb

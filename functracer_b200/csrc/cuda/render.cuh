@@ -764,11 +764,16 @@ FTB_DEV bool csgPair(const DevScene<R>& S, int leafA, int leafB, int op, const R
             for (int l = first; l < end; ++l) { h.cur = l; intersectLeaf<R, FEAT & ~FT_MESH, STATS>(S, l, wr, h, cn); }
             if (h.n > 2) return false;
             if (side) b = h; else a = h;
+            if (side == 0 && h.n == 0 && (op == OP_SUBTRACT || op == OP_INTERSECT)) return true;  // see below
         }
     } else {
         a.clear(leafA); b.clear(leafB);
         intersectLeaf<R, FEAT & ~FT_MESH, STATS>(S, leafA, wr, a, cn);
         if (a.n > 2) return false;
+        // A ray that never crosses A is never inside A: `subtract A B` and `intersect A B` then discard every crossing of B
+        // (OutsideIntoB / BIntoOutside -> Discard in both rule tables, Csg.fs:27-44), so B need not be intersected at all.  The
+        // bounding sphere of a cube lets many such rays through.
+        if (a.n == 0 && (op == OP_SUBTRACT || op == OP_INTERSECT)) return true;
         intersectLeaf<R, FEAT & ~FT_MESH, STATS>(S, leafB, wr, b, cn);
         if (b.n > 2) return false;
     }
@@ -1367,7 +1372,7 @@ __global__ void __launch_bounds__(kBlockThreads, MinBlocks<FEAT>::value) render_
                         const int sub = (int)(c & ((1u << bpt_log) - 1u));
                         const int tpos = (int)(c >> bpt_log);
                         const int ltile = F.tile_order ? __ldg(F.tile_order + tpos) : tpos;  // costliest tiles first
-                        const int tile = ltile * F.shard_count + F.shard_index;
+                        const int tile = tileOfLocal(ltile, F.shard_index, F.shard_count);
                         const int sx = (sub & ((1 << bpr_log) - 1)) << F.bw_log, sy = (sub >> bpr_log) << F.bh_log;
                         const int tile_y = F.tiles_x_magic ? (int)__umulhi((unsigned)tile, F.tiles_x_magic) : tile / F.tiles_x;
                         blk_x0 = (tile - tile_y * F.tiles_x) * FTB_TILE_W + sx;
