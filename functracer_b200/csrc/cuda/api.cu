@@ -685,6 +685,16 @@ int launchFrame(ftb_scene* sc, PerDevice* pd, const ftb_camera* cam, const ftb_r
         CK(cudaMemcpyAsync(pd->jitter.p, j, sizeof(j), cudaMemcpyHostToDevice, stream));
         F.jitter = static_cast<const R*>(pd->jitter.p);
     }
+    {  // |jitter . (pw i, ph j)| at its largest (i, j orthonormal): how far a sample's direction is from its pixel centre's
+        double reach = 0.0;
+        const int nj = g.corner ? 1 : g.spp;
+        for (int k = 0; k < nj; ++k) {
+            const double jx = g.corner ? -0.5 : p->jitter_xy[2 * k], jy = g.corner ? 0.5 : p->jitter_xy[2 * k + 1];
+            const double r = std::sqrt(jx * (double)F.pw * jx * (double)F.pw + jy * (double)F.ph * jy * (double)F.ph);
+            reach = (r > reach || r != r) ? r : reach;
+        }
+        F.pixel_reach = (R)(reach * 1.000001);
+    }
     F.recursion_limit = p->recursion_limit;
     F.seed = p->seed;
     F.out = static_cast<R*>(d_tiles);

@@ -11,7 +11,10 @@ namespace ftb {
 constexpr int kHitCap = 32;    // per-ray CSG hit stack entries
 constexpr int kMaxLists = 12;  // per-ray CSG list stack depth
 constexpr int kBspStack = 64;  // per-ray mesh traversal stack
-constexpr int kBlockThreads = 128;
+#ifndef FTB_BLOCK_THREADS
+#define FTB_BLOCK_THREADS 128
+#endif
+constexpr int kBlockThreads = FTB_BLOCK_THREADS;
 // Most samples of one unit of the blend ring (render.cuh): a launch covers at most this many samples per pixel, frames with
 // more are rendered in several passes that continue the same left fold.  128 (FP32) / 64 (FP64) in general; 256 for the variants
 // of simple scenes (spheres / planes only: no cube, round leaf, mesh or CSG), whose samples are cheap: at 64 spp a 128-sample unit
@@ -151,6 +154,7 @@ struct DevFrame {
     R cam_o[3], cam_k[3], cam_i[3], cam_j[3];
     R pw, ph, tlx, tly;
     R primary_slack;  // 2e-4 |cam_o|: see the common-origin bound table in render.cuh
+    R pixel_reach;    // the longest jitter offset of the frame on the image plane: no sample's d is further from its pixel centre's
     int has_focus;
     R focal, tan_half_aperture;
     const R* jitter;     // 2 * spp

@@ -846,7 +846,7 @@ struct HitInfo {
 //   prologue); tabSlack = how far the ray's actual line can pass from that common point, as a distance along the ray.
 template <typename R, unsigned FEAT, bool STATS>
 FTB_DEV HitInfo<R> traceScene(const DevScene<R>& S, const Ray<R>& wr, R limit, bool any, int skipLeaf, const typename V4<R>::type* tab, R tabSlack, bool& overflow, Counters<STATS>& cn,
-                              unsigned tracing, int* wstack)
+                              unsigned tracing, int* wstack, bool havePre = false, unsigned pre = 0u)
 {
     typedef typename V4<R>::type R4;
     RaySink<R> best;
@@ -861,7 +861,9 @@ FTB_DEV HitInfo<R> traceScene(const DevScene<R>& S, const Ray<R>& wr, R limit, b
         // of its stall samples waiting on these two loads).
         const int n = min(32, S.n_items - base);
         unsigned cand = 0;
-        if (tab) {  // rays from a common origin: |oc|, the miss and the behind test fold into one threshold per (origin, item)
+        if (havePre) {  // a primary ray whose pixel's candidates were found when its unit was opened (n_items <= 32: one batch)
+            cand = pre;
+        } else if (tab) {  // rays from a common origin: |oc|, the miss and the behind test fold into one threshold per (origin, item)
 #pragma unroll kTableUnroll
             for (int j = 0; j < n; ++j) {
                 const R4 e = tab[base + j];  // xyz = centre - origin (origin - centre for a light: the ray points AT it), w = threshold
@@ -1222,14 +1224,57 @@ constexpr int kRingSlots = FTB_RING_SLOTS;
 #ifndef FTB_FAST_BOUNDS
 #define FTB_FAST_BOUNDS 1
 #endif
+#ifndef FTB_PIXEL_MASKS
+#define FTB_PIXEL_MASKS 1
+#endif
 
 // Folds a completed unit: every pixel's samples of this pass, in sample order, onto the running sum of the earlier
 // passes; the last pass divides by the frame's sample count (Array.average = fold (+) Zero, then DivideByInt;
-// Image.fs:112-116, CommonTypes.fs:43).  One (pixel, channel) per lane.
+// Image.fs:112-116, CommonTypes.fs:43).
+//   FP64 verification build, and passes of fewer than 16 samples: one (pixel, channel) per lane, the literal left fold.
+//   FP32 product build with >= 16 samples in the pass: a unit of 64-spp pixels is two pixels, i.e. six (pixel, channel)
+//   sums of 64 dependent additions with 26 lanes idle (5 % of the warp instructions of the 8K frames at 6.6 lanes).
+//   The samples of a (pixel, channel) are cut into G consecutive segments, one lane each; the segment sums are then
+//   added in segment order by the first lane of the group.  G and the segment length depend on the pass's sample
+//   count ONLY (not on the block shape, the shard or the band), so the frame is still bit-identical however it was
+//   dealt; against the literal fold the sum differs by FP32 rounding of the association, 1e-7 relative.
+#ifndef FTB_PAR_FOLD
+#define FTB_PAR_FOLD 1
+#endif
 template <typename R>
 __device__ __noinline__ void foldUnit(const R* col, const int* hdr, R* out, int scount, int spp, int s_base, int lane)
 {
     const int slot0 = hdr[0], w = hdr[1], p0 = hdr[2], np = hdr[3];
+    if constexpr (sizeof(R) == 4 && FTB_PAR_FOLD != 0) {
+        if (scount >= 16) {
+            const int glog = scount >= 32 ? 2 : 1, G = 1 << glog;
+            const int seg = (scount + G - 1) >> glog;
+            const int tasks = np * 3;
+            for (int i0 = 0; i0 < (tasks << glog); i0 += 32) {  // warp-uniform
+                const int i = i0 + lane, task = i >> glog, part = i & (G - 1);
+                R acc = R(0);
+                long long o = 0;
+                if (task < tasks) {
+                    const int pix = task / 3, ch = task - 3 * pix;
+                    const int pj = p0 + pix;
+                    const int ly = pj / w;
+                    o = 3 * ((long long)slot0 + ly * FTB_TILE_W + (pj - ly * w)) + ch;
+                    if (part == 0 && s_base > 0) acc = out[o];  // a later pass continues the fold of the earlier ones
+                    const int q0 = part * seg, q1 = min(scount, q0 + seg);
+                    const R* c = col + 3 * (pix * scount) + ch;
+#pragma unroll 4
+                    for (int q = q0; q < q1; ++q) acc = acc + c[3 * q];
+                }
+                R total = acc;
+                for (int k = 1; k < G; ++k) total = total + __shfl_sync(0xffffffffu, acc, (lane & ~(G - 1)) + k);
+                if (task < tasks && part == 0) {
+                    if (s_base + scount >= spp) total = total / (R)spp;
+                    out[o] = total;
+                }
+            }
+            return;
+        }
+    }
     for (int i = lane; i < np * 3; i += 32) {
         const int pix = i / 3, ch = i - 3 * pix;
         const int pj = p0 + pix;
@@ -1251,9 +1296,11 @@ __global__ void __launch_bounds__(kBlockThreads, MinBlocks<FEAT>::value) render_
     constexpr int CAP = UnitCap<R, FEAT>::value;
     constexpr int WARPS = kBlockThreads / 32;
     __shared__ R ring_col[WARPS][kRingSlots][CAP * 3];
-    __shared__ int ring_hdr[WARPS][kRingSlots][4];  // out slot of the block's pixel 0, block width, first pixel, pixel count
-    __shared__ int mesh_stack[MeshWalks<FEAT>::kPacket ? WARPS : 1][MeshWalks<FEAT>::kPacket ? kBspStack : 1];  // packetMesh: one walk per warp
     constexpr bool kTable = FTB_FAST_BOUNDS != 0 && (FEAT & FT_TABLE) != 0;
+    constexpr bool kPixelMasks = kTable && FTB_PIXEL_MASKS != 0;
+    // out slot of the block's pixel 0, block width, first pixel, pixel count [, the primary-ray candidate items of each pixel of the unit]
+    __shared__ int ring_hdr[WARPS][kRingSlots][kPixelMasks ? 36 : 4];
+    __shared__ int mesh_stack[MeshWalks<FEAT>::kPacket ? WARPS : 1][MeshWalks<FEAT>::kPacket ? kBspStack : 1];  // packetMesh: one walk per warp
     __shared__ R4 origin_tab[kTable ? kOriginCap : 1];
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -1278,6 +1325,13 @@ __global__ void __launch_bounds__(kBlockThreads, MinBlocks<FEAT>::value) render_
     const int n_origins = 1 + S.n_lights;
     const bool fastBounds = kTable && S.n_items >= kOriginMinItems && n_origins * S.n_items <= kOriginCap;  // = wantsOriginTable
     const bool fastPrimary = fastBounds && F.mode == 0 && !((FEAT & FT_RNG) != 0 && F.has_focus);
+    // Per-pixel candidates for primary rays.  All samples of a pixel leave the camera within one pixel's width of the ray
+    // through the pixel's centre, so the bound tests of the common-origin table are made ONCE per pixel when its unit is
+    // opened (one lane per pixel of the unit, against the centre ray, every threshold widened by how far a sample's unit
+    // direction can be from the centre's: |du_s - du_c| <= 2 |d_s - d_c| / |d_c|, |d_c| >= 1, |d_s - d_c| <= F.pixel_reach =
+    // the longest jitter offset on the image plane; times |oc| in the dot product), instead of once per sample: a 64-spp
+    // frame makes 1/64 of the tests, a 4-spp one 1/4.  Like every bound test it may keep a miss but never drops a hit.
+    const bool pixelMasks = kPixelMasks && fastPrimary && S.n_items <= 32;
     if (fastBounds) {
         for (int o = 0; o < n_origins; ++o) {
             R4 org;
@@ -1309,7 +1363,7 @@ __global__ void __launch_bounds__(kBlockThreads, MinBlocks<FEAT>::value) render_
 
     // per-lane sample / path state
     // where this lane's sample is parked, in one register (the kernel is register-bound: every register saved is a spill less):
-    // bits 0..11 = position in the slot, bits 12..15 = ring slot, bits 16.. = samples left in this lane's run
+    // bits 0..11 = position in the slot, bits 12..15 = ring slot, bits 16..19 = samples left in this lane's run, bits 20..24 = pixel within the unit
     int rpos = 0;
     int px = 0, py = 0, sj = 0;      // pixel, sample index within the pixel
     // Index of the sample in the reference's full-frame ray list (RNG key, debug planes, explicit-ray index).  Variants with
@@ -1396,6 +1450,30 @@ __global__ void __launch_bounds__(kBlockThreads, MinBlocks<FEAT>::value) render_
                 if (lane == 0) {
                     ring_hdr[wib][u_slot][0] = blk_slot0; ring_hdr[wib][u_slot][1] = blk_w; ring_hdr[wib][u_slot][2] = u_p0; ring_hdr[wib][u_slot][3] = np;
                 }
+                if constexpr (kPixelMasks) {
+                    if (pixelMasks) {
+                        unsigned pm = 0;
+                        if (lane < np) {
+                            const int pj = u_p0 + lane;
+                            const int ly = blk_w == 8 ? (pj >> 3) : pj / blk_w;
+                            const R cx = F.tlx + (R)(blk_x0 + (pj - ly * blk_w)) * F.pw, cy = F.tly - (R)(blk_y0 + ly) * F.ph;
+                            const Vec<R> d = (mk<R>(F.cam_k[0], F.cam_k[1], F.cam_k[2]) + cx * mk<R>(F.cam_i[0], F.cam_i[1], F.cam_i[2])) + cy * mk<R>(F.cam_j[0], F.cam_j[1], F.cam_j[2]);
+                            const R il = R(1) / sqrt_(dot(d, d));
+                            const Vec<R> du = mk<R>(d.x * il, d.y * il, d.z * il);
+                            const R widen = R(2.02) * F.pixel_reach;
+#pragma unroll kTableUnroll
+                            for (int j = 0; j < S.n_items; ++j) {
+                                const R4 e = origin_tab[j];
+                                const R reach = sqrt_(e.x * e.x + e.y * e.y + e.z * e.z) * widen + F.primary_slack;
+                                const R b = e.x * du.x + (e.y * du.y + (e.z * du.z + reach));
+                                cn.add(ST_BOUND_FAST, e.w > -inf_<R>() ? 1u : 0u);
+                                pm |= !(b < e.w) ? (1u << j) : 0u;
+                            }
+                        }
+                        ring_hdr[wib][u_slot][4 + lane] = (int)pm;
+                        __syncwarp();
+                    }
+                }
             }
             const int rank = __popc(m & lt_mask);
             const int avail = u_n - u_pos;
@@ -1404,7 +1482,7 @@ __global__ void __launch_bounds__(kBlockThreads, MinBlocks<FEAT>::value) render_
                 const int pu = rpp == 1 ? q : (int)__umulhi((unsigned)q, F.rpp_magic);  // pixel within the unit = q / rpp
                 const int pj = u_p0 + pu;                                        // pixel within the block
                 sj = F.s_base + (q - pu * rpp) * run;
-                rpos = (q * run) | (u_slot << 12) | (run << 16);
+                rpos = (q * run) | (u_slot << 12) | (run << 16) | (pu << 20);
                 if (F.mode == 0) {
                     const int ly = blk_w == 8 ? (pj >> 3) : pj / blk_w;
                     px = blk_x0 + (pj - ly * blk_w); py = blk_y0 + ly;
@@ -1463,10 +1541,18 @@ __global__ void __launch_bounds__(kBlockThreads, MinBlocks<FEAT>::value) render_
         if constexpr (sizeof(R) == 4 && (FEAT & FT_PLANAR) != 0) {  // `f` is still the fragment this bounce / shadow ray starts from
             if (f.planarLeaf >= 0 && (phase == PH_NEAREST ? limit < F.recursion_limit : dot(ray.d, f.n) >= R(0))) skipLeaf = f.planarLeaf;
         }
+        bool havePre = false;
+        unsigned pre = 0u;
+        if constexpr (kPixelMasks) {
+            if (pixelMasks && phase == PH_NEAREST && limit == F.recursion_limit) {
+                havePre = true;
+                pre = (unsigned)ring_hdr[wib][(rpos >> 12) & 0xf][4 + ((rpos >> 20) & 0x1f)];
+            }
+        }
         const HitInfo<R> h = traceScene<R, FEAT, STATS>(S, tr, phase == PH_NEAREST ? inf_<R>() : tmax, phase == PH_SHADOW, skipLeaf,
                                                         tabled ? origin_tab + (phase == PH_NEAREST ? 0 : 1 + li) * S.n_items : nullptr,
                                                         phase == PH_NEAREST ? F.primary_slack : R(4e-4) * tmax,
-                                                        overflow, cn, tracing, &mesh_stack[MeshWalks<FEAT>::kPacket ? wib : 0][0]);
+                                                        overflow, cn, tracing, &mesh_stack[MeshWalks<FEAT>::kPacket ? wib : 0][0], havePre, pre);
 
         // ---- consume the result -----------------------------------------------------------------------------------------
         bool got = false;       // an intensity for light `li` is ready
@@ -1491,7 +1577,7 @@ __global__ void __launch_bounds__(kBlockThreads, MinBlocks<FEAT>::value) render_
                 c[0] = scol.x; c[1] = scol.y; c[2] = scol.z;
                 retire = true;
                 rpos -= 0xffff;  // one sample fewer in the run, one position further
-                if ((rpos >> 16) > 0) { ++sj; if constexpr (kCarryIndex) ++sampleIndex; phase = PH_START; } else phase = PH_IDLE;
+                if (((rpos >> 16) & 0xf) > 0) { ++sj; if constexpr (kCarryIndex) ++sampleIndex; phase = PH_START; } else phase = PH_IDLE;
                 continue;
             }
             cn.add(ST_SHADED);
@@ -1566,7 +1652,7 @@ __global__ void __launch_bounds__(kBlockThreads, MinBlocks<FEAT>::value) render_
             c[0] = scol.x; c[1] = scol.y; c[2] = scol.z;
             retire = true;
             rpos -= 0xffff;  // one sample fewer in the run, one position further
-            if ((rpos >> 16) > 0) { ++sj; if constexpr (kCarryIndex) ++sampleIndex; phase = PH_START; } else phase = PH_IDLE;
+            if (((rpos >> 16) & 0xf) > 0) { ++sj; if constexpr (kCarryIndex) ++sampleIndex; phase = PH_START; } else phase = PH_IDLE;
         }
     }
     if (overflow) atomicExch(F.overflow, 1u);

@@ -2,7 +2,8 @@
 // persistent megakernel (selected at run time with FTB_WAVEFRONT=1; DESIGN.md §8, BENCH.md §4).
 //
 // The same device functions (traceScene, finalise, shadeLight, primaryRay, jitterVector) in the same order per sample - so a frame
-// is BIT-IDENTICAL to the megakernel's - but split into one kernel per stage, with every path's state and every ray living in
+// equals the megakernel's up to the last bits of FP32 (primary hits identical; the compiler contracts multiply-adds differently
+// in different kernels, and the megakernel folds long sample runs in segments) - but split into one kernel per stage, with every path's state and every ray living in
 // structure-of-arrays records in HBM between the stages:
 //   generate   primary rays of a wave of samples (all samples of a run of tiles)          -> path records
 //   nearest    nearest-hit query of every live path (Scene.closest, Scene.fs:112-118)      -> hit records
