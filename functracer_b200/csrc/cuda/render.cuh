@@ -36,6 +36,9 @@
 namespace ftb {
 
 #define FTB_DEV __device__ __forceinline__
+#ifndef FTB_PUSH_SINK
+#define FTB_PUSH_SINK 1
+#endif
 
 // ---- scalar helpers -------------------------------------------------------------------------------
 FTB_DEV float min_(float a, float b) { return fminf(a, b); }
@@ -567,30 +570,45 @@ FTB_DEV void intersectLeaf(const DevScene<R>& S, int leaf, const Ray<R>& wr, Sin
 }
 
 // ---- sinks ----------------------------------------------------------------------------------------------
+constexpr int kIdSubShiftI = 22, kIdFlipI = 1 << 30, kIdLeafMaskI = (1 << 22) - 1;  // = kIdSubShift, kIdFlip, kIdLeafMask below
 // Scene.closest (Scene.fs:112-116): smallest t >= 0, first in enumeration order on ties — and, with
 // `limit` preset to maxDistance and `any` set, Scene.lightIsBocked (Scene.fs:119-121) for leaves whose
 // surface has applyLighting = true: any hit with 0 <= t < maxDistance.
-template <typename R>
+// The winner lives in one register: id = leaf | sub << 22 | flip << 30 (-1: none).  Variants with meshes (WIDE) keep the
+// sub-id - a triangle index there - in a register of its own.  A hit site of the leaf intersectors is then two compares
+// and two selects.
+template <typename R, bool WIDE>
 struct RaySink {
     static constexpr bool kIsRay = true;
     R limit;
-    int leaf, sub, flip;
+    int id, sub;  // sub: WIDE only (dead otherwise)
     int cur;  // leaf being intersected
     bool any;
     bool overflow;
     FTB_DEV void hit(R ht, int hsub)
     {
-        if (ht >= R(0) && ht < limit) { limit = ht; leaf = cur; sub = hsub; flip = 0; }
+        if (ht >= R(0) && ht < limit) take(ht, cur, hsub, false);
     }
-    FTB_DEV bool done() const { return any && leaf >= 0; }
+    FTB_DEV void take(R ht, int leaf, int hsub, bool flip)
+    {
+        limit = ht;
+        id = leaf | (WIDE ? 0 : ((hsub & 7) << kIdSubShiftI)) | (flip ? (int)kIdFlipI : 0);
+        if (WIDE) sub = hsub;
+    }
+    FTB_DEV void block(int leaf) { id = leaf; }  // Scene.lightIsBocked: which leaf does not matter
+    FTB_DEV bool found() const { return id >= 0; }
+    FTB_DEV int leaf() const { return id < 0 ? -1 : (id & (WIDE ? 0x3fffffff : (int)kIdLeafMaskI)); }
+    FTB_DEV int subId() const { return WIDE ? sub : ((id >> kIdSubShiftI) & 7); }
+    FTB_DEV int flipped() const { return (id >> 30) & 1; }
+    FTB_DEV bool done() const { return any && found(); }
 };
 // A mesh item's answer, found after the other items of its batch (traceScene): it also wins a tie in t against a winner
 // that comes LATER in the enumeration, as Scene.closest's stable sort would have it.
-template <typename R>
-FTB_DEV void meshHit(RaySink<R>& best, int& bestItem, int item, int leaf, R ht, int tri)
+template <typename R, bool WIDE>
+FTB_DEV void meshHit(RaySink<R, WIDE>& best, int& bestItem, int item, int leaf, R ht, int tri)
 {
-    if (ht >= R(0) && (ht < best.limit || (ht == best.limit && best.leaf >= 0 && item < bestItem))) {
-        best.limit = ht; best.leaf = leaf; best.sub = tri; best.flip = 0; bestItem = item;
+    if (ht >= R(0) && (ht < best.limit || (ht == best.limit && best.found() && item < bestItem))) {
+        best.take(ht, leaf, tri, false); bestItem = item;
     }
 }
 // CSG operand: append to the per-ray hit stack.
@@ -726,6 +744,24 @@ __device__ __noinline__ CsgAnswer<R> csgGeneral(const DevScene<R>* S, int opFirs
 template <typename R, bool RUNS>
 struct PairSink {
     static constexpr bool kIsRay = false;
+#if FTB_PUSH_SINK
+    // The last two crossings, newest first (a push is four moves and no compare at every hit site of the leaf intersectors;
+    // which one was first is sorted out once, in csgPair): n == 1: (t0, i0); n == 2: (t1, i1) then (t0, i0).
+    R t0, t1;
+    unsigned i0, i1;  // leaf | sub << kIdSubShift
+    int n, cur;
+    FTB_DEV void clear(int first) { n = 0; t0 = t1 = R(0); i0 = i1 = 0u; cur = first; }
+    FTB_DEV void hit(R ht, int hsub)
+    {
+        t1 = t0; i1 = i0;
+        t0 = ht; i0 = (unsigned)cur | ((unsigned)(hsub & 7) << 22);
+        ++n;
+    }
+    FTB_DEV R firstT() const { return n > 1 ? t1 : t0; }
+    FTB_DEV unsigned firstId() const { return n > 1 ? i1 : i0; }
+    FTB_DEV R secondT() const { return t0; }
+    FTB_DEV unsigned secondId() const { return i0; }
+#else
     R t0, t1;
     int s0, s1, n;
     int cur, l0, l1;  // RUNS only (dead otherwise)
@@ -735,6 +771,11 @@ struct PairSink {
         if (n == 0) { t0 = ht; s0 = hsub; if (RUNS) l0 = cur; } else if (n == 1) { t1 = ht; s1 = hsub; if (RUNS) l1 = cur; }
         ++n;
     }
+    FTB_DEV R firstT() const { return t0; }
+    FTB_DEV unsigned firstId() const { return (unsigned)l0 | ((unsigned)(s0 & 7) << 22); }
+    FTB_DEV R secondT() const { return t1; }
+    FTB_DEV unsigned secondId() const { return (unsigned)l1 | ((unsigned)(s1 & 7) << 22); }
+#endif
     FTB_DEV bool done() const { return false; }
 };
 
@@ -748,7 +789,7 @@ struct PairSink {
 //   (sphere)` is the only CSG item of house / night-house / repeat) walk both operands' runs through ONE copy, which
 //   keeps those scenes off the general evaluator and its local-memory hit stack (measured -6 % house, -8 % repeat).
 template <typename R, unsigned FEAT, bool STATS>
-FTB_DEV bool csgPair(const DevScene<R>& S, int leafA, int leafB, int op, const Ray<R>& wr, RaySink<R>& best, Counters<STATS>& cn)
+FTB_DEV bool csgPair(const DevScene<R>& S, int leafA, int leafB, int op, const Ray<R>& wr, RaySink<R, (FEAT & FT_MESH) != 0>& best, Counters<STATS>& cn)
 {
     constexpr bool RUNS = (FEAT & FT_PAIRG) != 0;
     PairSink<R, RUNS> a, b;
@@ -785,10 +826,10 @@ FTB_DEV bool csgPair(const DevScene<R>& S, int leafA, int leafB, int op, const R
     constexpr unsigned kInvalid = 0xffffffffu;
     R mt[4];
     unsigned mid[4];
-    mt[0] = a.n > 0 ? a.t0 : inf_<R>(); mid[0] = a.n > 0 ? ((unsigned)(RUNS ? a.l0 : leafA) | ((unsigned)(a.s0 & 7) << kIdSubShift)) : kInvalid;
-    mt[1] = a.n > 1 ? a.t1 : inf_<R>(); mid[1] = a.n > 1 ? ((unsigned)(RUNS ? a.l1 : leafA) | ((unsigned)(a.s1 & 7) << kIdSubShift)) : kInvalid;
-    mt[2] = b.n > 0 ? b.t0 : inf_<R>(); mid[2] = b.n > 0 ? ((unsigned)(RUNS ? b.l0 : leafB) | ((unsigned)(b.s0 & 7) << kIdSubShift) | kIdSideB) : kInvalid;
-    mt[3] = b.n > 1 ? b.t1 : inf_<R>(); mid[3] = b.n > 1 ? ((unsigned)(RUNS ? b.l1 : leafB) | ((unsigned)(b.s1 & 7) << kIdSubShift) | kIdSideB) : kInvalid;
+    mt[0] = a.n > 0 ? a.firstT() : inf_<R>(); mid[0] = a.n > 0 ? a.firstId() : kInvalid;
+    mt[1] = a.n > 1 ? a.secondT() : inf_<R>(); mid[1] = a.n > 1 ? a.secondId() : kInvalid;
+    mt[2] = b.n > 0 ? b.firstT() : inf_<R>(); mid[2] = b.n > 0 ? (b.firstId() | kIdSideB) : kInvalid;
+    mt[3] = b.n > 1 ? b.secondT() : inf_<R>(); mid[3] = b.n > 1 ? (b.secondId() | kIdSideB) : kInvalid;
     auto cx = [&](int i, int j) {
         const bool sw = mt[j] < mt[i];
         const R ti = mt[i], tj = mt[j];
@@ -810,12 +851,12 @@ FTB_DEV bool csgPair(const DevScene<R>& S, int leafA, int leafB, int op, const R
             if (rule != 1u && ht >= R(0)) {
                 const int leaf = (int)(id & kIdLeafMask);
                 if (!best.any) {  // the item's first crossing with t >= 0 is its candidate (Scene.closest)
-                    if (ht < best.limit) { best.limit = ht; best.leaf = leaf; best.sub = (int)((id >> kIdSubShift) & 7u); best.flip = rule == 2u ? 1 : 0; }
+                    if (ht < best.limit) best.take(ht, leaf, (int)((id >> kIdSubShift) & 7u), rule == 2u);
                     decided = true;
                 } else if (!(ht < best.limit)) {
                     decided = true;
                 } else if (__ldg(S.surf_i + __ldg(S.leaf_meta + leaf).y).z) {  // Scene.lightIsBocked: applyLighting surfaces only
-                    best.leaf = leaf;
+                    best.block(leaf);
                     decided = true;
                 }
             }
@@ -849,8 +890,8 @@ FTB_DEV HitInfo<R> traceScene(const DevScene<R>& S, const Ray<R>& wr, R limit, b
                               unsigned tracing, int* wstack, bool havePre = false, unsigned pre = 0u)
 {
     typedef typename V4<R>::type R4;
-    RaySink<R> best;
-    best.limit = limit; best.leaf = -1; best.sub = 0; best.flip = 0; best.any = any; best.cur = 0; best.overflow = false;
+    RaySink<R, (FEAT & FT_MESH) != 0> best;
+    best.limit = limit; best.id = -1; best.sub = 0; best.any = any; best.cur = 0; best.overflow = false;
     int bestItem = -1;  // mesh variants: the item of the current winner (tie rule of meshHit)
     // unit direction for the bound tests (their slack covers its rounding)
     const R inv_len = R(1) / sqrt_(dot(wr.d, wr.d));
@@ -916,56 +957,52 @@ FTB_DEV HitInfo<R> traceScene(const DevScene<R>& S, const Ray<R>& wr, R limit, b
                             const R ht = stack[k].t;
                             if (!(ht >= R(0))) continue;
                             if (!any) {  // the first t >= 0 is this item's candidate; it wins if it beats best
-                                if (ht < best.limit) {
-                                    best.limit = ht; best.leaf = (int)(stack[k].id & kIdLeafMask); best.sub = (int)((stack[k].id >> kIdSubShift) & 7u);
-                                    best.flip = (stack[k].id & kIdFlip) ? 1 : 0;
-                                }
+                                if (ht < best.limit) best.take(ht, (int)(stack[k].id & kIdLeafMask), (int)((stack[k].id >> kIdSubShift) & 7u), (stack[k].id & kIdFlip) != 0);
                                 break;
                             }
                             if (!(ht < best.limit)) break;
                             const int leaf = (int)(stack[k].id & kIdLeafMask);
-                            if (__ldg(S.surf_i + __ldg(S.leaf_meta + leaf).y).z) { best.leaf = leaf; break; }
+                            if (__ldg(S.surf_i + __ldg(S.leaf_meta + leaf).y).z) { best.block(leaf); break; }
                         }
                     } else {  // pair-only scenes: the rare fallback stays out of line, off the hot loop's instruction footprint
                         const CsgAnswer<R> ans = csgGeneral<R, FEAT, STATS>(&S, prog.x, prog.y, wr, best.limit, any, STATS ? &cn : nullptr);
                         if (ans.leaf >= 0) {
-                            best.leaf = ans.leaf;
-                            if (!any) { best.limit = ans.t; best.sub = ans.sub; best.flip = ans.flip; }
+                            if (any) best.block(ans.leaf); else best.take(ans.t, ans.leaf, ans.sub, ans.flip != 0);
                         }
                         best.overflow = best.overflow || ans.overflow;
                     }
                 }
             }
             if constexpr (MeshWalks<FEAT>::kPacket) { if (best.limit < before) bestItem = it; }
-            if (any && best.leaf >= 0) cand = 0;
+            if (any && best.found()) cand = 0;
         }
         if (kPacket && packet) {
             // every lane of the call is here (the batch loop is warp-uniform in this mode): the meshes any lane still wants
-            unsigned todo = __reduce_or_sync(tracing, (any && best.leaf >= 0) ? 0u : meshCand);
+            unsigned todo = __reduce_or_sync(tracing, (any && best.found()) ? 0u : meshCand);
             while (todo) {
                 const int j = __ffs(todo) - 1;
                 todo &= todo - 1;
                 const int it = base + j;
                 const int leaf = __ldg(S.items + it).y;
                 const int4 meta = __ldg(S.leaf_meta + leaf);
-                const bool want = ((meshCand >> j) & 1u) && !(any && best.leaf >= 0);
+                const bool want = ((meshCand >> j) & 1u) && !(any && best.found());
                 const Ray<R> r = toModel(S, leaf, (meta.x >> 8) & 1, wr);
                 if (want) { cn.add(ST_LEAF0 + LEAF_MESH); if (!((meta.x >> 8) & 1)) cn.add(ST_XFORM); }
                 R bt; int btri;
                 packetMesh<R, STATS>(S, __ldg(S.mesh_root + meta.w), r, best.limit, any, want, tracing, wstack, bt, btri, cn);
                 if (want && btri >= 0) {
-                    if (any) best.leaf = leaf;  // t < limit held inside the walk
+                    if (any) best.block(leaf);  // t < limit held inside the walk
                     else meshHit(best, bestItem, it, leaf, bt, btri);
                 }
             }
-            if (__all_sync(tracing, any && best.leaf >= 0)) break;
+            if (__all_sync(tracing, any && best.found())) break;
         } else {
-            if (any && best.leaf >= 0) break;
+            if (any && best.found()) break;
         }
     }
     overflow = overflow || best.overflow;
     HitInfo<R> h;
-    h.t = best.limit; h.leaf = best.leaf; h.sub = best.sub; h.flip = best.flip;
+    h.t = best.limit; h.leaf = best.leaf(); h.sub = best.subId(); h.flip = best.flipped();
     return h;
 }
 
@@ -1225,29 +1262,36 @@ constexpr int kRingSlots = FTB_RING_SLOTS;
 #define FTB_FAST_BOUNDS 1
 #endif
 #ifndef FTB_PIXEL_MASKS
-#define FTB_PIXEL_MASKS 1
+#define FTB_PIXEL_MASKS 0
+#endif
+#ifndef FTB_SHADOW_TABLE
+#define FTB_SHADOW_TABLE 1
 #endif
 
 // Folds a completed unit: every pixel's samples of this pass, in sample order, onto the running sum of the earlier
 // passes; the last pass divides by the frame's sample count (Array.average = fold (+) Zero, then DivideByInt;
 // Image.fs:112-116, CommonTypes.fs:43).
-//   FP64 verification build, and passes of fewer than 16 samples: one (pixel, channel) per lane, the literal left fold.
-//   FP32 product build with >= 16 samples in the pass: a unit of 64-spp pixels is two pixels, i.e. six (pixel, channel)
-//   sums of 64 dependent additions with 26 lanes idle (5 % of the warp instructions of the 8K frames at 6.6 lanes).
-//   The samples of a (pixel, channel) are cut into G consecutive segments, one lane each; the segment sums are then
-//   added in segment order by the first lane of the group.  G and the segment length depend on the pass's sample
-//   count ONLY (not on the block shape, the shard or the band), so the frame is still bit-identical however it was
-//   dealt; against the literal fold the sum differs by FP32 rounding of the association, 1e-7 relative.
+//   FP64 verification build, and units of more than 5 pixels (passes of < 26 samples): one (pixel, channel) per lane, the
+//   literal left fold.
+//   FP32 product build, long passes: a unit of 64-spp pixels is two pixels, i.e. six (pixel, channel) sums of 64
+//   dependent additions with 26 lanes idle (5 % of the warp instructions of the 8K frames at 6.6 lanes).  The samples
+//   of a (pixel, channel) are cut into G = 2 or 4 consecutive segments, one lane each; the segment sums are then added
+//   in segment order by the first lane of the group.  G and the segment length depend on the pass's sample count and
+//   the variant's unit size ONLY (not on the block shape, the shard or the band), so the frame is still bit-identical
+//   however it was dealt; against the literal fold the sum differs by FP32 rounding of the association, 1e-7 relative.
 #ifndef FTB_PAR_FOLD
 #define FTB_PAR_FOLD 1
 #endif
 template <typename R>
-__device__ __noinline__ void foldUnit(const R* col, const int* hdr, R* out, int scount, int spp, int s_base, int lane)
+__device__ __noinline__ void foldUnit(const R* col, const int* hdr, R* out, int scount, int spp, int s_base, int lane, int cap)
 {
     const int slot0 = hdr[0], w = hdr[1], p0 = hdr[2], np = hdr[3];
     if constexpr (sizeof(R) == 4 && FTB_PAR_FOLD != 0) {
-        if (scount >= 16) {
-            const int glog = scount >= 32 ? 2 : 1, G = 1 << glog;
+        // G = the most segments that still fold a full unit (cap / scount pixels x 3 channels) in one round of the warp
+        const int full3 = 3 * max(1, min(32, cap / scount));
+        const int glog = 4 * full3 <= 32 ? 2 : (2 * full3 <= 32 ? 1 : 0);
+        if (glog > 0) {
+            const int G = 1 << glog;
             const int seg = (scount + G - 1) >> glog;
             const int tasks = np * 3;
             for (int i0 = 0; i0 < (tasks << glog); i0 += 32) {  // warp-uniform
@@ -1400,7 +1444,7 @@ __global__ void __launch_bounds__(kBlockThreads, MinBlocks<FEAT>::value) render_
             while (doneSlots) {  // rare relative to the trace: one out-of-line copy keeps the hot loop small
                 const int k = __ffs(doneSlots) - 1;
                 doneSlots &= doneSlots - 1;
-                foldUnit<R>(&ring_col[wib][k][0], &ring_hdr[wib][k][0], F.out, scount, spp, F.s_base, lane);
+                foldUnit<R>(&ring_col[wib][k][0], &ring_hdr[wib][k][0], F.out, scount, spp, F.s_base, lane, CAP);
             }
             retire = false;
             __syncwarp();
@@ -1520,7 +1564,7 @@ __global__ void __launch_bounds__(kBlockThreads, MinBlocks<FEAT>::value) render_
         // all lanes that trace in this iteration have a row in the common-origin table?  (warp-uniform)
         bool tabled = false;
         if (fastBounds) {
-            const bool mine = phase == PH_NEAREST ? (fastPrimary && limit == F.recursion_limit) : tmax < realmax_<R>();  // finite tmax: a point light
+            const bool mine = phase == PH_NEAREST ? (fastPrimary && limit == F.recursion_limit) : (FTB_SHADOW_TABLE != 0 && tmax < realmax_<R>());  // finite tmax: a point light
             tabled = !__any_sync(full, phase != PH_IDLE && !hold && !mine);
         }
         unsigned tracing = full;  // variants with the packet walk: the lanes that trace a ray in this iteration
@@ -1550,7 +1594,7 @@ __global__ void __launch_bounds__(kBlockThreads, MinBlocks<FEAT>::value) render_
             }
         }
         const HitInfo<R> h = traceScene<R, FEAT, STATS>(S, tr, phase == PH_NEAREST ? inf_<R>() : tmax, phase == PH_SHADOW, skipLeaf,
-                                                        tabled ? origin_tab + (phase == PH_NEAREST ? 0 : 1 + li) * S.n_items : nullptr,
+                                                        (kPixelMasks && FTB_SHADOW_TABLE == 0) ? nullptr : (tabled ? origin_tab + (phase == PH_NEAREST ? 0 : 1 + li) * S.n_items : nullptr),
                                                         phase == PH_NEAREST ? F.primary_slack : R(4e-4) * tmax,
                                                         overflow, cn, tracing, &mesh_stack[MeshWalks<FEAT>::kPacket ? wib : 0][0], havePre, pre);
 
