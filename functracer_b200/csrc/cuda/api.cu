@@ -354,8 +354,9 @@ int uploadScene(const ftb_scene& sc, SceneStorage<R>& st)
             items.push_back(make_int4(it.kind, it.a, it.b, it.casts_shadow));
             progs.push_back(make_int2(it.prog_first, it.prog_count));
             // conservative: radius inflated by 0.2 % + 1e-5 so that FP32 rounding of the test cannot cull a true hit
+            // unbounded items (planes) carry r^2 = +inf: no line misses them and no origin is outside them
             const double ri = it.bound_r < 0 ? -1.0 : it.bound_r * 1.002 + 1e-5;
-            bounds.push_back(Mk4<R>::make(it.bound_c[0], it.bound_c[1], it.bound_c[2], ri < 0 ? -1.0 : ri * ri));
+            bounds.push_back(Mk4<R>::make(it.bound_c[0], it.bound_c[1], it.bound_c[2], ri < 0 ? (double)INFINITY : ri * ri));
         }
         for (const CsgOp& op : L.ops) ops.push_back(make_int2(op.kind, op.arg));
         std::vector<unsigned> casts((L.items.size() + 31) / 32 + 1, 0u);
@@ -684,16 +685,6 @@ int launchFrame(ftb_scene* sc, PerDevice* pd, const ftb_camera* cam, const ftb_r
         CK(pd->jitter.reserve(sizeof(j)));
         CK(cudaMemcpyAsync(pd->jitter.p, j, sizeof(j), cudaMemcpyHostToDevice, stream));
         F.jitter = static_cast<const R*>(pd->jitter.p);
-    }
-    {  // |jitter . (pw i, ph j)| at its largest (i, j orthonormal): how far a sample's direction is from its pixel centre's
-        double reach = 0.0;
-        const int nj = g.corner ? 1 : g.spp;
-        for (int k = 0; k < nj; ++k) {
-            const double jx = g.corner ? -0.5 : p->jitter_xy[2 * k], jy = g.corner ? 0.5 : p->jitter_xy[2 * k + 1];
-            const double r = std::sqrt(jx * (double)F.pw * jx * (double)F.pw + jy * (double)F.ph * jy * (double)F.ph);
-            reach = (r > reach || r != r) ? r : reach;
-        }
-        F.pixel_reach = (R)(reach * 1.000001);
     }
     F.recursion_limit = p->recursion_limit;
     F.seed = p->seed;

@@ -103,7 +103,7 @@ struct DevScene {
     // top-level items in enumeration order
     const int4* items;     // x = kind (| op << 8 for ITEM_CSG2), y = a, z = b, w = casts_shadow
     const int2* item_prog; // CSG items: x = first op, y = op count of the general program
-    const R4* item_bound;  // xyz = centre, w = (inflated radius)^2 of a conservative bounding sphere (< 0 unbounded)
+    const R4* item_bound;  // xyz = centre, w = (inflated radius)^2 of a conservative bounding sphere (+inf: unbounded)
     const unsigned* item_casts;  // bit j of word w: item 32 w + j can block light (something under it has applyLighting)
     const unsigned* item_mesh;   // bit j of word w: item 32 w + j is a mesh leaf
     int mesh_packet;             // 1: mesh leaves are walked by the whole warp (render.cuh packetMesh; large meshes), 0: by each lane (intersectMesh)
@@ -154,7 +154,6 @@ struct DevFrame {
     R cam_o[3], cam_k[3], cam_i[3], cam_j[3];
     R pw, ph, tlx, tly;
     R primary_slack;  // 2e-4 |cam_o|: see the common-origin bound table in render.cuh
-    R pixel_reach;    // the longest jitter offset of the frame on the image plane: no sample's d is further from its pixel centre's
     int has_focus;
     R focal, tan_half_aperture;
     const R* jitter;     // 2 * spp

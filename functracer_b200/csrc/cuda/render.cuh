@@ -36,9 +36,6 @@
 namespace ftb {
 
 #define FTB_DEV __device__ __forceinline__
-#ifndef FTB_PUSH_SINK
-#define FTB_PUSH_SINK 1
-#endif
 
 // ---- scalar helpers -------------------------------------------------------------------------------
 FTB_DEV float min_(float a, float b) { return fminf(a, b); }
@@ -247,11 +244,11 @@ FTB_DEV bool planeT(const Ray<R>& r, R& t, Vec<R>& p)
     const R eps = R(0.0000001);
     R num = -r.o.y;
     R denom = r.d.y;
-    if (abs_(denom) < eps) {
-        if (num < eps) { t = R(0); p = r.o; return true; }
-        return false;
-    }
     t = num / denom;
+    if (abs_(denom) < eps) {  // parallel: the reference answers t = 0, p = o when the origin is on or below the plane (Plane.fs:13-16)
+        if (!(num < eps)) return false;
+        t = R(0);  // p below = o + 0 d = o for every finite d
+    }
     p = mk<R>(r.o.x + t * r.d.x, r.o.y + t * r.d.y, r.o.z + t * r.d.z);
     return true;
 }
@@ -744,7 +741,6 @@ __device__ __noinline__ CsgAnswer<R> csgGeneral(const DevScene<R>* S, int opFirs
 template <typename R, bool RUNS>
 struct PairSink {
     static constexpr bool kIsRay = false;
-#if FTB_PUSH_SINK
     // The last two crossings, newest first (a push is four moves and no compare at every hit site of the leaf intersectors;
     // which one was first is sorted out once, in csgPair): n == 1: (t0, i0); n == 2: (t1, i1) then (t0, i0).
     R t0, t1;
@@ -754,28 +750,13 @@ struct PairSink {
     FTB_DEV void hit(R ht, int hsub)
     {
         t1 = t0; i1 = i0;
-        t0 = ht; i0 = (unsigned)cur | ((unsigned)(hsub & 7) << 22);
+        t0 = ht; i0 = (unsigned)cur | ((unsigned)(hsub & 7) << kIdSubShiftI);
         ++n;
     }
     FTB_DEV R firstT() const { return n > 1 ? t1 : t0; }
     FTB_DEV unsigned firstId() const { return n > 1 ? i1 : i0; }
     FTB_DEV R secondT() const { return t0; }
     FTB_DEV unsigned secondId() const { return i0; }
-#else
-    R t0, t1;
-    int s0, s1, n;
-    int cur, l0, l1;  // RUNS only (dead otherwise)
-    FTB_DEV void clear(int first) { n = 0; t0 = t1 = R(0); s0 = s1 = 0; cur = l0 = l1 = first; }
-    FTB_DEV void hit(R ht, int hsub)
-    {
-        if (n == 0) { t0 = ht; s0 = hsub; if (RUNS) l0 = cur; } else if (n == 1) { t1 = ht; s1 = hsub; if (RUNS) l1 = cur; }
-        ++n;
-    }
-    FTB_DEV R firstT() const { return t0; }
-    FTB_DEV unsigned firstId() const { return (unsigned)l0 | ((unsigned)(s0 & 7) << 22); }
-    FTB_DEV R secondT() const { return t1; }
-    FTB_DEV unsigned secondId() const { return (unsigned)l1 | ((unsigned)(s1 & 7) << 22); }
-#endif
     FTB_DEV bool done() const { return false; }
 };
 
@@ -865,13 +846,23 @@ FTB_DEV bool csgPair(const DevScene<R>& S, int leafA, int leafB, int op, const R
     return true;
 }
 
-#ifndef FTB_BOUND_UNROLL
-#define FTB_BOUND_UNROLL 4  // measured: 1, 2 and 8 are slower (the loads and arithmetic of neighbouring items overlap)
+// bit 31 = "x < 0".  FP32: the sign bit itself (a - b < 0 <=> a < b: the sign of a rounded difference is the sign of the exact one,
+// flush-to-zero keeps it; -0 cannot come out of a subtraction or an FMA with a non-zero sum; a NaN result is the canonical,
+// positive one: "not less", like the comparison).  The FP64 verification build compares.
+FTB_DEV unsigned signWord(float x) { return __float_as_uint(x); }
+FTB_DEV unsigned signWord(double x) { return x < 0.0 ? 0x80000000u : 0u; }
+// Unrolling of the two bound loops, per variant (measured, profiles/r2t_*): 4 for the small kernels (hollow-sphere -1 % against 1,
+// moon -1 %: the loads and arithmetic of neighbouring items overlap), 1 for the large ones (house -2.3 %, night-house -2.4 %,
+// repeat -0.5 %, the 960-triangle mesh -1.9 %: 240 SASS instructions fewer in kernels whose limiter is instruction fetch).
+// The general loop builds its mask from sign bits like the table loop in the variants with the heavy leaf classes (house -2.4 %,
+// night-house -2.8 %, repeat -1.9 %, hollow-sphere -1.2 %); the simple scenes and the mesh-only variants keep the compares (moon +3 %,
+// the 960-triangle mesh +0.7 % with the signs).
+template <unsigned FEAT> struct BoundSigns { static constexpr bool value = (FEAT & (FT_CUBE | FT_ROUND | FT_CSG | FT_CSGN)) != 0; };
+#ifdef FTB_BOUND_UNROLL
+template <unsigned FEAT> struct BoundUnroll { static constexpr int value = FTB_BOUND_UNROLL; };
+#else
+template <unsigned FEAT> struct BoundUnroll { static constexpr int value = (FEAT & (FT_PAIRG | FT_CSGN | FT_MESH)) != 0 ? 1 : 4; };
 #endif
-#ifndef FTB_TABLE_UNROLL
-#define FTB_TABLE_UNROLL 4
-#endif
-constexpr int kBoundUnroll = FTB_BOUND_UNROLL, kTableUnroll = FTB_TABLE_UNROLL;  // (#pragma unroll takes constants, not macros)
 
 template <typename R>
 struct HitInfo {
@@ -887,9 +878,10 @@ struct HitInfo {
 //   prologue); tabSlack = how far the ray's actual line can pass from that common point, as a distance along the ray.
 template <typename R, unsigned FEAT, bool STATS>
 FTB_DEV HitInfo<R> traceScene(const DevScene<R>& S, const Ray<R>& wr, R limit, bool any, int skipLeaf, const typename V4<R>::type* tab, R tabSlack, bool& overflow, Counters<STATS>& cn,
-                              unsigned tracing, int* wstack, bool havePre = false, unsigned pre = 0u)
+                              unsigned tracing, int* wstack)
 {
     typedef typename V4<R>::type R4;
+    constexpr int kUnroll = BoundUnroll<FEAT>::value;  // (#pragma unroll takes constants, not macros)
     RaySink<R, (FEAT & FT_MESH) != 0> best;
     best.limit = limit; best.id = -1; best.sub = 0; best.any = any; best.cur = 0; best.overflow = false;
     int bestItem = -1;  // mesh variants: the item of the current winner (tie rule of meshHit)
@@ -902,29 +894,47 @@ FTB_DEV HitInfo<R> traceScene(const DevScene<R>& S, const Ray<R>& wr, R limit, b
         // of its stall samples waiting on these two loads).
         const int n = min(32, S.n_items - base);
         unsigned cand = 0;
-        if (havePre) {  // a primary ray whose pixel's candidates were found when its unit was opened (n_items <= 32: one batch)
-            cand = pre;
-        } else if (tab) {  // rays from a common origin: |oc|, the miss and the behind test fold into one threshold per (origin, item)
-#pragma unroll kTableUnroll
-            for (int j = 0; j < n; ++j) {
+        if (tab) {  // rays from a common origin: |oc|, the miss and the behind test fold into one threshold per (origin, item)
+            // candidate <=> !(b < w) <=> the sign bit of b - w is clear (a NaN is the canonical, positive one; w = -inf gives +inf):
+            // the items are walked from the last to the first and each sign is shifted into the mask by one funnel shift.
+            unsigned out = 0;
+#pragma unroll kUnroll
+            for (int j = n - 1; j >= 0; --j) {
                 const R4 e = tab[base + j];  // xyz = centre - origin (origin - centre for a light: the ray points AT it), w = threshold
-                const R b = e.x * du.x + (e.y * du.y + (e.z * du.z + tabSlack));
+                const R bw = e.x * du.x + (e.y * du.y + (e.z * du.z + (tabSlack - e.w)));
                 cn.add(ST_BOUND_FAST, e.w > -inf_<R>() ? 1u : 0u);
-                cand |= !(b < e.w) ? (1u << j) : 0u;  // NaN stays a candidate, like the general form
+                out = __funnelshift_l(signWord(bw), out, 1);
             }
+            cand = ~out & (n >= 32 ? 0xffffffffu : ((1u << n) - 1u));
         } else {
-#pragma unroll kBoundUnroll
-            for (int j = 0; j < n; ++j) {
-                const R4 bound = ldg4<R>(S.item_bound + base + j);  // xyz = centre, w = inflated radius^2 (< 0: unbounded)
-                const Vec<R> oc = mk<R>(bound.x - wr.o.x, bound.y - wr.o.y, bound.z - wr.o.z);
-                const R b = dot(oc, du);                                 // distance along the ray to the point nearest the centre
-                const R oc2 = dot(oc, oc);
-                // |centre - line|^2 = oc2 - b^2; the 1e-6 oc2 slack covers the cancellation (and the radius is inflated)
-                const bool miss = oc2 - b * b > bound.w + R(1e-6) * oc2;  // the ray's line misses the bound: no crossing at all
-                const bool behind = b < R(0) && oc2 > bound.w;            // bound entirely behind the origin: every crossing has t < 0
-                const bool unbounded = bound.w < R(0);
-                cn.add(ST_BOUND_TESTS, unbounded ? 0u : 1u);
-                cand |= (unbounded || !(miss || behind)) ? (1u << j) : 0u;
+            if constexpr (BoundSigns<FEAT>::value) {
+                unsigned out = 0;
+#pragma unroll kUnroll
+                for (int j = n - 1; j >= 0; --j) {
+                    const R4 bound = ldg4<R>(S.item_bound + base + j);  // xyz = centre, w = inflated radius^2 (+inf: unbounded)
+                    const Vec<R> oc = mk<R>(bound.x - wr.o.x, bound.y - wr.o.y, bound.z - wr.o.z);
+                    const R b = dot(oc, du);                                 // distance along the ray to the point nearest the centre
+                    const R oc2 = dot(oc, oc);
+                    // |centre - line|^2 = oc2 - b^2; the 1e-6 oc2 slack covers the cancellation (and the radius is inflated)
+                    const R miss = (bound.w + R(1e-6) * oc2) - (oc2 - b * b);  // < 0: the ray's line misses the bound: no crossing at all
+                    const R outside = bound.w - oc2;                           // < 0 and b < 0: bound entirely behind the origin, every crossing has t < 0
+                    cn.add(ST_BOUND_TESTS, bound.w < inf_<R>() ? 1u : 0u);
+                    out = __funnelshift_l(signWord(miss) | (signWord(b) & signWord(outside)), out, 1);  // w = +inf: neither can be negative
+                }
+                cand = ~out & (n >= 32 ? 0xffffffffu : ((1u << n) - 1u));
+            } else {
+#pragma unroll kUnroll
+                for (int j = 0; j < n; ++j) {
+                    const R4 bound = ldg4<R>(S.item_bound + base + j);  // xyz = centre, w = inflated radius^2 (+inf: unbounded)
+                    const Vec<R> oc = mk<R>(bound.x - wr.o.x, bound.y - wr.o.y, bound.z - wr.o.z);
+                    const R b = dot(oc, du);                                 // distance along the ray to the point nearest the centre
+                    const R oc2 = dot(oc, oc);
+                    // |centre - line|^2 = oc2 - b^2; the 1e-6 oc2 slack covers the cancellation (and the radius is inflated)
+                    const bool miss = oc2 - b * b > bound.w + R(1e-6) * oc2;  // the ray's line misses the bound: no crossing at all
+                    const bool behind = b < R(0) && oc2 > bound.w;            // bound entirely behind the origin: every crossing has t < 0
+                    cn.add(ST_BOUND_TESTS, bound.w < inf_<R>() ? 1u : 0u);
+                    cand |= !(miss || behind) ? (1u << j) : 0u;                // w = +inf: neither
+                }
             }
         }
         if (any) cand &= __ldg(S.item_casts + (base >> 5));  // items with nothing that has applyLighting cannot block (Scene.fs:121)
@@ -1261,63 +1271,48 @@ constexpr int kRingSlots = FTB_RING_SLOTS;
 #ifndef FTB_FAST_BOUNDS
 #define FTB_FAST_BOUNDS 1
 #endif
-#ifndef FTB_PIXEL_MASKS
-#define FTB_PIXEL_MASKS 0
-#endif
-#ifndef FTB_SHADOW_TABLE
-#define FTB_SHADOW_TABLE 1
-#endif
 
 // Folds a completed unit: every pixel's samples of this pass, in sample order, onto the running sum of the earlier
 // passes; the last pass divides by the frame's sample count (Array.average = fold (+) Zero, then DivideByInt;
 // Image.fs:112-116, CommonTypes.fs:43).
-//   FP64 verification build, and units of more than 5 pixels (passes of < 26 samples): one (pixel, channel) per lane, the
-//   literal left fold.
-//   FP32 product build, long passes: a unit of 64-spp pixels is two pixels, i.e. six (pixel, channel) sums of 64
-//   dependent additions with 26 lanes idle (5 % of the warp instructions of the 8K frames at 6.6 lanes).  The samples
-//   of a (pixel, channel) are cut into G = 2 or 4 consecutive segments, one lane each; the segment sums are then added
-//   in segment order by the first lane of the group.  G and the segment length depend on the pass's sample count and
-//   the variant's unit size ONLY (not on the block shape, the shard or the band), so the frame is still bit-identical
-//   however it was dealt; against the literal fold the sum differs by FP32 rounding of the association, 1e-7 relative.
-#ifndef FTB_PAR_FOLD
-#define FTB_PAR_FOLD 1
-#endif
+//   quads == 0 (the FP64 verification build; units of more than two pixels): one (pixel, channel) per lane, the literal
+//   left fold.
+//   quads != 0 (FP32 product build, units of one or two pixels = passes of >= 43 / >= 86 samples): a unit of 64-spp pixels
+//   is two pixels, i.e. six sums of 64 dependent additions with 26 lanes idle (5 % of the warp instructions of the 8K
+//   repeat frame at 6.6 lanes).  The samples of a (pixel, channel) are cut into four consecutive segments, one lane each;
+//   the segment sums are then added in segment order by the first lane of the four.  Whether and how a pixel's samples
+//   are segmented depends on the pass's sample count and the variant's unit size ONLY (not on the block shape, the shard
+//   or the band), so the frame is still bit-identical however it was dealt; against the literal fold the sum differs by
+//   FP32 rounding of the association, 1e-7 relative.  Measured: repeat -3.8 %; two segments for four-pixel units (moon)
+//   did not pay (+1.2 %).
 template <typename R>
-__device__ __noinline__ void foldUnit(const R* col, const int* hdr, R* out, int scount, int spp, int s_base, int lane, int cap)
+__device__ __noinline__ void foldUnit(const R* col, const int* hdr, R* out, int scount, int spp, int s_base, int lane, int quads)
 {
     const int slot0 = hdr[0], w = hdr[1], p0 = hdr[2], np = hdr[3];
-    if constexpr (sizeof(R) == 4 && FTB_PAR_FOLD != 0) {
-        // G = the most segments that still fold a full unit (cap / scount pixels x 3 channels) in one round of the warp
-        const int full3 = 3 * max(1, min(32, cap / scount));
-        const int glog = 4 * full3 <= 32 ? 2 : (2 * full3 <= 32 ? 1 : 0);
-        if (glog > 0) {
-            const int G = 1 << glog;
-            const int seg = (scount + G - 1) >> glog;
-            const int tasks = np * 3;
-            for (int i0 = 0; i0 < (tasks << glog); i0 += 32) {  // warp-uniform
-                const int i = i0 + lane, task = i >> glog, part = i & (G - 1);
-                R acc = R(0);
-                long long o = 0;
-                if (task < tasks) {
-                    const int pix = task / 3, ch = task - 3 * pix;
-                    const int pj = p0 + pix;
-                    const int ly = pj / w;
-                    o = 3 * ((long long)slot0 + ly * FTB_TILE_W + (pj - ly * w)) + ch;
-                    if (part == 0 && s_base > 0) acc = out[o];  // a later pass continues the fold of the earlier ones
-                    const int q0 = part * seg, q1 = min(scount, q0 + seg);
-                    const R* c = col + 3 * (pix * scount) + ch;
+    if (quads) {
+        const int seg = (scount + 3) >> 2;
+        const int i = lane, task = i >> 2, part = i & 3;  // np <= 2: 6 tasks x 4 lanes fit one round
+        R acc = R(0);
+        long long o = 0;
+        if (task < np * 3) {
+            const int pix = task / 3, ch = task - 3 * pix;
+            const int pj = p0 + pix;
+            const int ly = pj / w;
+            o = 3 * ((long long)slot0 + ly * FTB_TILE_W + (pj - ly * w)) + ch;
+            if (part == 0 && s_base > 0) acc = out[o];  // a later pass continues the fold of the earlier ones
+            const int q0 = part * seg, q1 = min(scount, q0 + seg);
+            const R* c = col + 3 * (pix * scount) + ch;
 #pragma unroll 4
-                    for (int q = q0; q < q1; ++q) acc = acc + c[3 * q];
-                }
-                R total = acc;
-                for (int k = 1; k < G; ++k) total = total + __shfl_sync(0xffffffffu, acc, (lane & ~(G - 1)) + k);
-                if (task < tasks && part == 0) {
-                    if (s_base + scount >= spp) total = total / (R)spp;
-                    out[o] = total;
-                }
-            }
-            return;
+            for (int q = q0; q < q1; ++q) acc = acc + c[3 * q];
         }
+        R total = acc;
+#pragma unroll
+        for (int k = 1; k < 4; ++k) total = total + __shfl_sync(0xffffffffu, acc, (lane & ~3) + k);
+        if (task < np * 3 && part == 0) {
+            if (s_base + scount >= spp) total = total / (R)spp;
+            out[o] = total;
+        }
+        return;
     }
     for (int i = lane; i < np * 3; i += 32) {
         const int pix = i / 3, ch = i - 3 * pix;
@@ -1341,9 +1336,7 @@ __global__ void __launch_bounds__(kBlockThreads, MinBlocks<FEAT>::value) render_
     constexpr int WARPS = kBlockThreads / 32;
     __shared__ R ring_col[WARPS][kRingSlots][CAP * 3];
     constexpr bool kTable = FTB_FAST_BOUNDS != 0 && (FEAT & FT_TABLE) != 0;
-    constexpr bool kPixelMasks = kTable && FTB_PIXEL_MASKS != 0;
-    // out slot of the block's pixel 0, block width, first pixel, pixel count [, the primary-ray candidate items of each pixel of the unit]
-    __shared__ int ring_hdr[WARPS][kRingSlots][kPixelMasks ? 36 : 4];
+    __shared__ int ring_hdr[WARPS][kRingSlots][4];  // out slot of the block's pixel 0, block width, first pixel, pixel count
     __shared__ int mesh_stack[MeshWalks<FEAT>::kPacket ? WARPS : 1][MeshWalks<FEAT>::kPacket ? kBspStack : 1];  // packetMesh: one walk per warp
     __shared__ R4 origin_tab[kTable ? kOriginCap : 1];
     const unsigned full = 0xffffffffu;
@@ -1369,13 +1362,6 @@ __global__ void __launch_bounds__(kBlockThreads, MinBlocks<FEAT>::value) render_
     const int n_origins = 1 + S.n_lights;
     const bool fastBounds = kTable && S.n_items >= kOriginMinItems && n_origins * S.n_items <= kOriginCap;  // = wantsOriginTable
     const bool fastPrimary = fastBounds && F.mode == 0 && !((FEAT & FT_RNG) != 0 && F.has_focus);
-    // Per-pixel candidates for primary rays.  All samples of a pixel leave the camera within one pixel's width of the ray
-    // through the pixel's centre, so the bound tests of the common-origin table are made ONCE per pixel when its unit is
-    // opened (one lane per pixel of the unit, against the centre ray, every threshold widened by how far a sample's unit
-    // direction can be from the centre's: |du_s - du_c| <= 2 |d_s - d_c| / |d_c|, |d_c| >= 1, |d_s - d_c| <= F.pixel_reach =
-    // the longest jitter offset on the image plane; times |oc| in the dot product), instead of once per sample: a 64-spp
-    // frame makes 1/64 of the tests, a 4-spp one 1/4.  Like every bound test it may keep a miss but never drops a hit.
-    const bool pixelMasks = kPixelMasks && fastPrimary && S.n_items <= 32;
     if (fastBounds) {
         for (int o = 0; o < n_origins; ++o) {
             R4 org;
@@ -1388,7 +1374,7 @@ __global__ void __launch_bounds__(kBlockThreads, MinBlocks<FEAT>::value) render_
                 const R k = dot(v, v) * R(1.0 - 8e-6) - bound.w;
                 R4 row;
                 row.x = v.x; row.y = v.y; row.z = v.z;
-                row.w = (bound.w < R(0) || !(k > R(0))) ? -inf_<R>() : sqrt_(k);
+                row.w = !(k > R(0)) ? -inf_<R>() : sqrt_(k);  // unbounded items (w = +inf) and origins inside the bound: always candidates
                 origin_tab[o * S.n_items + j] = row;
             }
         }
@@ -1407,7 +1393,7 @@ __global__ void __launch_bounds__(kBlockThreads, MinBlocks<FEAT>::value) render_
 
     // per-lane sample / path state
     // where this lane's sample is parked, in one register (the kernel is register-bound: every register saved is a spill less):
-    // bits 0..11 = position in the slot, bits 12..15 = ring slot, bits 16..19 = samples left in this lane's run, bits 20..24 = pixel within the unit
+    // bits 0..11 = position in the slot, bits 12..15 = ring slot, bits 16.. = samples left in this lane's run
     int rpos = 0;
     int px = 0, py = 0, sj = 0;      // pixel, sample index within the pixel
     // Index of the sample in the reference's full-frame ray list (RNG key, debug planes, explicit-ray index).  Variants with
@@ -1430,6 +1416,7 @@ __global__ void __launch_bounds__(kBlockThreads, MinBlocks<FEAT>::value) render_
     const int run = F.mode == 0 ? F.run : 1;          // consecutive samples of one pixel a lane takes at a time (divides scount)
     const int rpp = scount / run;                     // runs per pixel
     const int ppu = max(1, min(32, CAP / scount));    // pixels per unit
+    const int foldQuads = (sizeof(R) == 4 && ppu <= 2) ? 1 : 0;  // see foldUnit
 
     for (;;) {
         // ---- fold units whose last sample has landed (colours were parked when each path ended) ---------------------
@@ -1444,7 +1431,7 @@ __global__ void __launch_bounds__(kBlockThreads, MinBlocks<FEAT>::value) render_
             while (doneSlots) {  // rare relative to the trace: one out-of-line copy keeps the hot loop small
                 const int k = __ffs(doneSlots) - 1;
                 doneSlots &= doneSlots - 1;
-                foldUnit<R>(&ring_col[wib][k][0], &ring_hdr[wib][k][0], F.out, scount, spp, F.s_base, lane, CAP);
+                foldUnit<R>(&ring_col[wib][k][0], &ring_hdr[wib][k][0], F.out, scount, spp, F.s_base, lane, foldQuads);
             }
             retire = false;
             __syncwarp();
@@ -1494,30 +1481,6 @@ __global__ void __launch_bounds__(kBlockThreads, MinBlocks<FEAT>::value) render_
                 if (lane == 0) {
                     ring_hdr[wib][u_slot][0] = blk_slot0; ring_hdr[wib][u_slot][1] = blk_w; ring_hdr[wib][u_slot][2] = u_p0; ring_hdr[wib][u_slot][3] = np;
                 }
-                if constexpr (kPixelMasks) {
-                    if (pixelMasks) {
-                        unsigned pm = 0;
-                        if (lane < np) {
-                            const int pj = u_p0 + lane;
-                            const int ly = blk_w == 8 ? (pj >> 3) : pj / blk_w;
-                            const R cx = F.tlx + (R)(blk_x0 + (pj - ly * blk_w)) * F.pw, cy = F.tly - (R)(blk_y0 + ly) * F.ph;
-                            const Vec<R> d = (mk<R>(F.cam_k[0], F.cam_k[1], F.cam_k[2]) + cx * mk<R>(F.cam_i[0], F.cam_i[1], F.cam_i[2])) + cy * mk<R>(F.cam_j[0], F.cam_j[1], F.cam_j[2]);
-                            const R il = R(1) / sqrt_(dot(d, d));
-                            const Vec<R> du = mk<R>(d.x * il, d.y * il, d.z * il);
-                            const R widen = R(2.02) * F.pixel_reach;
-#pragma unroll kTableUnroll
-                            for (int j = 0; j < S.n_items; ++j) {
-                                const R4 e = origin_tab[j];
-                                const R reach = sqrt_(e.x * e.x + e.y * e.y + e.z * e.z) * widen + F.primary_slack;
-                                const R b = e.x * du.x + (e.y * du.y + (e.z * du.z + reach));
-                                cn.add(ST_BOUND_FAST, e.w > -inf_<R>() ? 1u : 0u);
-                                pm |= !(b < e.w) ? (1u << j) : 0u;
-                            }
-                        }
-                        ring_hdr[wib][u_slot][4 + lane] = (int)pm;
-                        __syncwarp();
-                    }
-                }
             }
             const int rank = __popc(m & lt_mask);
             const int avail = u_n - u_pos;
@@ -1526,7 +1489,7 @@ __global__ void __launch_bounds__(kBlockThreads, MinBlocks<FEAT>::value) render_
                 const int pu = rpp == 1 ? q : (int)__umulhi((unsigned)q, F.rpp_magic);  // pixel within the unit = q / rpp
                 const int pj = u_p0 + pu;                                        // pixel within the block
                 sj = F.s_base + (q - pu * rpp) * run;
-                rpos = (q * run) | (u_slot << 12) | (run << 16) | (pu << 20);
+                rpos = (q * run) | (u_slot << 12) | (run << 16);
                 if (F.mode == 0) {
                     const int ly = blk_w == 8 ? (pj >> 3) : pj / blk_w;
                     px = blk_x0 + (pj - ly * blk_w); py = blk_y0 + ly;
@@ -1564,7 +1527,7 @@ __global__ void __launch_bounds__(kBlockThreads, MinBlocks<FEAT>::value) render_
         // all lanes that trace in this iteration have a row in the common-origin table?  (warp-uniform)
         bool tabled = false;
         if (fastBounds) {
-            const bool mine = phase == PH_NEAREST ? (fastPrimary && limit == F.recursion_limit) : (FTB_SHADOW_TABLE != 0 && tmax < realmax_<R>());  // finite tmax: a point light
+            const bool mine = phase == PH_NEAREST ? (fastPrimary && limit == F.recursion_limit) : tmax < realmax_<R>();  // finite tmax: a point light
             tabled = !__any_sync(full, phase != PH_IDLE && !hold && !mine);
         }
         unsigned tracing = full;  // variants with the packet walk: the lanes that trace a ray in this iteration
@@ -1585,18 +1548,10 @@ __global__ void __launch_bounds__(kBlockThreads, MinBlocks<FEAT>::value) render_
         if constexpr (sizeof(R) == 4 && (FEAT & FT_PLANAR) != 0) {  // `f` is still the fragment this bounce / shadow ray starts from
             if (f.planarLeaf >= 0 && (phase == PH_NEAREST ? limit < F.recursion_limit : dot(ray.d, f.n) >= R(0))) skipLeaf = f.planarLeaf;
         }
-        bool havePre = false;
-        unsigned pre = 0u;
-        if constexpr (kPixelMasks) {
-            if (pixelMasks && phase == PH_NEAREST && limit == F.recursion_limit) {
-                havePre = true;
-                pre = (unsigned)ring_hdr[wib][(rpos >> 12) & 0xf][4 + ((rpos >> 20) & 0x1f)];
-            }
-        }
         const HitInfo<R> h = traceScene<R, FEAT, STATS>(S, tr, phase == PH_NEAREST ? inf_<R>() : tmax, phase == PH_SHADOW, skipLeaf,
-                                                        (kPixelMasks && FTB_SHADOW_TABLE == 0) ? nullptr : (tabled ? origin_tab + (phase == PH_NEAREST ? 0 : 1 + li) * S.n_items : nullptr),
+                                                        tabled ? origin_tab + (phase == PH_NEAREST ? 0 : 1 + li) * S.n_items : nullptr,
                                                         phase == PH_NEAREST ? F.primary_slack : R(4e-4) * tmax,
-                                                        overflow, cn, tracing, &mesh_stack[MeshWalks<FEAT>::kPacket ? wib : 0][0], havePre, pre);
+                                                        overflow, cn, tracing, &mesh_stack[MeshWalks<FEAT>::kPacket ? wib : 0][0]);
 
         // ---- consume the result -----------------------------------------------------------------------------------------
         bool got = false;       // an intensity for light `li` is ready
@@ -1621,7 +1576,7 @@ __global__ void __launch_bounds__(kBlockThreads, MinBlocks<FEAT>::value) render_
                 c[0] = scol.x; c[1] = scol.y; c[2] = scol.z;
                 retire = true;
                 rpos -= 0xffff;  // one sample fewer in the run, one position further
-                if (((rpos >> 16) & 0xf) > 0) { ++sj; if constexpr (kCarryIndex) ++sampleIndex; phase = PH_START; } else phase = PH_IDLE;
+                if ((rpos >> 16) > 0) { ++sj; if constexpr (kCarryIndex) ++sampleIndex; phase = PH_START; } else phase = PH_IDLE;
                 continue;
             }
             cn.add(ST_SHADED);
@@ -1696,7 +1651,7 @@ __global__ void __launch_bounds__(kBlockThreads, MinBlocks<FEAT>::value) render_
             c[0] = scol.x; c[1] = scol.y; c[2] = scol.z;
             retire = true;
             rpos -= 0xffff;  // one sample fewer in the run, one position further
-            if (((rpos >> 16) & 0xf) > 0) { ++sj; if constexpr (kCarryIndex) ++sampleIndex; phase = PH_START; } else phase = PH_IDLE;
+            if ((rpos >> 16) > 0) { ++sj; if constexpr (kCarryIndex) ++sampleIndex; phase = PH_START; } else phase = PH_IDLE;
         }
     }
     if (overflow) atomicExch(F.overflow, 1u);

@@ -98,7 +98,7 @@ FTB_DEV bool wfOriginTable(const DevScene<R>& S, const DevFrame<R>& F, typename 
                 const R k = dot(v, v) * R(1.0 - 8e-6) - bound.w;
                 R4 row;
                 row.x = v.x; row.y = v.y; row.z = v.z;
-                row.w = (bound.w < R(0) || !(k > R(0))) ? -inf_<R>() : sqrt_(k);
+                row.w = !(k > R(0)) ? -inf_<R>() : sqrt_(k);
                 origin_tab[o * S.n_items + j] = row;
             }
         }

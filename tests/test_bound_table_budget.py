@@ -2,7 +2,7 @@
 
 The kernel answers "can this ray touch item j at all?" for primary rays and point-light shadow rays with
 
-    b = row.xyz . unit(d) + slack  >=  row.w,     row = (centre - origin, sqrt(|oc|^2 (1 - 8e-6) - w)),  w = inflated r^2
+    row.xyz . unit(d) + (slack - row.w)  >=  0,    row = (centre - origin, sqrt(|oc|^2 (1 - 8e-6) - w)),  w = inflated r^2
 
 in FP32.  This test replays that arithmetic in numpy float32 (separate roundings instead of FMAs, the reciprocal square
 root perturbed by +-2 ulp like MUFU.RSQ) on rays aimed at the silhouettes of randomly placed bounding spheres, over the
@@ -40,7 +40,7 @@ def _row(centre32, origin32, w32, sign, rng=None):
     v = (F(sign) * (centre32 - origin32)).astype(F)
     vv = (v[:, 0] * v[:, 0] + v[:, 1] * v[:, 1] + v[:, 2] * v[:, 2]).astype(F)
     k = (vv * F(1.0 - 8e-6) - w32).astype(F)
-    s = np.where((w32 < 0) | ~(k > 0), F(-np.inf), np.sqrt(np.maximum(k, F(0))).astype(F)).astype(F)  # w < 0: unbounded item
+    s = np.where(~(k > 0), F(-np.inf), np.sqrt(np.maximum(k, F(0))).astype(F)).astype(F)  # w = +inf (unbounded item) gives k = -inf
     if rng is not None:
         s = (s * (F(1) + rng.uniform(-2.4e-7, 2.4e-7, size=s.shape).astype(F))).astype(F)
     return v, s
@@ -55,10 +55,12 @@ def _unit32(d32, rng):
 
 
 def _candidate(v, s, du, slack32):
-    b = (v[:, 2] * du[:, 2] + slack32).astype(F)
+    """traceScene's table loop: the sign of b - w with b - w = v.x du.x + (v.y du.y + (v.z du.z + (slack - w)))"""
+    b = (slack32 - s).astype(F)
+    b = (v[:, 2] * du[:, 2] + b).astype(F)
     b = (v[:, 1] * du[:, 1] + b).astype(F)
     b = (v[:, 0] * du[:, 0] + b).astype(F)
-    return ~(b < s)
+    return ~np.signbit(b) | np.isnan(b)
 
 
 def _eps(rng, n):
@@ -161,7 +163,7 @@ def test_origin_inside_or_unbounded_is_always_a_candidate():
     centre = (cam.astype(np.float64) + _rand_dirs(rng, n) * (r * rng.uniform(0, 0.999, size=n))[:, None]).astype(F)  # camera inside
     v, s = _row(centre, cam, _inflated_r2(r), +1)
     assert np.isneginf(s).all()
-    v, s = _row(centre, cam, np.full(n, -1.0, dtype=F), +1)  # unbounded items carry w = -1
+    v, s = _row(centre, cam, np.full(n, np.inf, dtype=F), +1)  # unbounded items carry w = +inf
     assert np.isneginf(s).all()
     du = _unit32(_rand_dirs(rng, n).astype(F), rng)
     assert _candidate(v, s, du, np.zeros(n, dtype=F)).all()

@@ -51,3 +51,35 @@ def test_random_with_ties():
         slots = [(pool[0], "a0" if na > 0 else None), (pool[1], "a1" if na > 1 else None),
                  (pool[2], "b0" if nb > 0 else None), (pool[3], "b1" if nb > 1 else None)]
         assert by_insertion(slots) == by_network(slots), slots
+
+
+class _PushSink:
+    """render.cuh PairSink: the last two crossings, newest first; csgPair reads them back in emission order."""
+
+    def __init__(self):
+        self.n, self.t0, self.t1, self.i0, self.i1 = 0, 0.0, 0.0, None, None
+
+    def hit(self, t, ident):
+        self.t1, self.i1 = self.t0, self.i0
+        self.t0, self.i0 = t, ident
+        self.n += 1
+
+    def slots(self):
+        first = (self.t1, self.i1) if self.n > 1 else (self.t0, self.i0)
+        return [first if self.n > 0 else (0.0, None), (self.t0, self.i0) if self.n > 1 else (0.0, None)]
+
+
+def test_push_front_sink_reads_back_in_emission_order():
+    rnd = random.Random(5)
+    for _ in range(2000):
+        a, b = _PushSink(), _PushSink()
+        na, nb = rnd.choice([0, 1, 2]), rnd.choice([0, 1, 2])
+        ha = [(rnd.choice([0.0, 1.0, 1.0, -2.0]), "a%d" % k) for k in range(na)]
+        hb = [(rnd.choice([0.0, 1.0, 1.0, -2.0]), "b%d" % k) for k in range(nb)]
+        for t, i in ha:
+            a.hit(t, i)
+        for t, i in hb:
+            b.hit(t, i)
+        emitted = [(t, i) for t, i in ha] + [(0.0, None)] * (2 - na) + [(t, i) for t, i in hb] + [(0.0, None)] * (2 - nb)
+        assert a.slots() + b.slots() == emitted
+        assert by_network(a.slots() + b.slots()) == by_insertion(emitted)
