@@ -351,7 +351,13 @@ int uploadScene(const ftb_scene& sc, SceneStorage<R>& st)
     {
         std::vector<int4> items; std::vector<R4> bounds; std::vector<int2> ops, progs;
         for (const Item& it : L.items) {
-            items.push_back(make_int4(it.kind, it.a, it.b, it.casts_shadow));
+            // kind | CSG op << 8 | kind word of leaf A << 12 | of leaf B << 21 (kind word = leaf kind | identity << 8, as in leaf_meta.x):
+            // the walk branches on a top-level leaf's / a pair operand's kind without waiting for the leaf's own record
+            auto kw = [&](int leaf) { const Leaf& lf = L.leaves[(size_t)(leaf & 0xffffff)]; return (lf.kind & 0xff) | (lf.identity ? 0x100 : 0); };
+            int kx = it.kind & 0xfff;
+            if ((it.kind & 0xff) == ITEM_LEAF) kx |= kw(it.a) << 12;
+            else if ((it.kind & 0xff) == ITEM_CSG2) kx |= (kw(it.a) << 12) | (kw(it.b) << 21);
+            items.push_back(make_int4(kx, it.a, it.b, it.casts_shadow));
             progs.push_back(make_int2(it.prog_first, it.prog_count));
             // conservative: radius inflated by 0.2 % + 1e-5 so that FP32 rounding of the test cannot cull a true hit
             // unbounded items (planes) carry r^2 = +inf: no line misses them and no origin is outside them

@@ -101,7 +101,7 @@ struct DevScene {
     const int4* leaf_meta;  // x = kind | identity << 8, y = surface, z = prim, w = payload
     int n_leaves;
     // top-level items in enumeration order
-    const int4* items;     // x = kind (| op << 8 for ITEM_CSG2), y = a, z = b, w = casts_shadow
+    const int4* items;     // x = kind | CSG op << 8 | kind word of leaf a << 12 | of leaf b << 21 (kind word: leaf_meta.x & 0x1ff), y = a, z = b, w = casts_shadow
     const int2* item_prog; // CSG items: x = first op, y = op count of the general program
     const R4* item_bound;  // xyz = centre, w = (inflated radius)^2 of a conservative bounding sphere (+inf: unbounded)
     const unsigned* item_casts;  // bit j of word w: item 32 w + j can block light (something under it has applyLighting)

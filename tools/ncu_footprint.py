@@ -12,9 +12,23 @@ import re
 import subprocess
 import sys
 
+
+
+def kernel_section(path, pattern=r"render_kernel.*Lb0"):
+    """The lines of the one function of an `nvdisasm -g -c` listing whose .text section name matches `pattern` (a cubin holds
+    several kernels, each with addresses from 0)."""
+    out, on = [], False
+    for ln in open(path):
+        if ln.startswith("//---------------------"):
+            on = re.search(pattern, ln) is not None
+            continue
+        if on:
+            out.append(ln)
+    return out or list(open(path))
+
 rep, sass, srcpath = sys.argv[1:4]
 addr_line, cur = {}, None
-for ln in open(sass):
+for ln in kernel_section(sass):
     m = re.search(r'//## File "([^"]+)", line (\d+)', ln)
     if m:
         cur = (m.group(1).split("/")[-1], int(m.group(2)))

@@ -4,16 +4,31 @@ same kernel (nvdisasm -g of a cubin built from the same source) and prints the h
 usage: ncu_hot_lines.py report.ncu-rep kernel.sass(from nvdisasm -g -c) [topN]"""
 import csv
 import io
+import os
 import re
 import subprocess
 import sys
 import collections
 
+
+
+def kernel_section(path, pattern=r"render_kernel.*Lb0"):
+    """The lines of the one function of an `nvdisasm -g -c` listing whose .text section name matches `pattern` (a cubin holds
+    several kernels, each with addresses from 0)."""
+    out, on = [], False
+    for ln in open(path):
+        if ln.startswith("//---------------------"):
+            on = re.search(pattern, ln) is not None
+            continue
+        if on:
+            out.append(ln)
+    return out or list(open(path))
+
 rep, sass = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
 addr_line = {}
 cur = None
-for ln in open(sass):
+for ln in kernel_section(sass):
     m = re.search(r'//## File "([^"]+)", line (\d+)', ln)
     if m:
         cur = (m.group(1).split("/")[-1], int(m.group(2)))
@@ -47,7 +62,8 @@ for r in rows[2:]:
 src = {}
 for f in set(k[0] for k in agg):
     try:
-        path = subprocess.run(["find", ".", "-name", f, "-not", "-path", "./.git/*"], stdout=subprocess.PIPE, text=True).stdout.split()[0]
+        # FTB_SRC_DIR: a directory holding the sources as they were when the profiled library was built
+        path = subprocess.run(["find", os.environ.get("FTB_SRC_DIR", "."), "-name", f, "-not", "-path", "./.git/*"], stdout=subprocess.PIPE, text=True).stdout.split()[0]
         src[f] = open(path).read().splitlines()
     except Exception:
         src[f] = []
