@@ -371,6 +371,13 @@ int uploadScene(const ftb_scene& sc, SceneStorage<R>& st)
         std::vector<unsigned> meshes(casts.size(), 0u);
         for (size_t i = 0; i < L.items.size(); ++i)
             if (L.items[i].kind == ITEM_LEAF && L.leaves[(size_t)L.items[i].a].kind == LEAF_MESH) meshes[i >> 5] |= 1u << (i & 31);
+        std::vector<R4> bounds2;  // pairs of neighbouring items interleaved (render.cuh: the packed bound test of the FP32 kernels)
+        for (size_t i = 0; i < bounds.size(); i += 2) {
+            const R4 a = bounds[i], b = i + 1 < bounds.size() ? bounds[i + 1] : Mk4<R>::make(0, 0, 0, (double)INFINITY);
+            bounds2.push_back(Mk4<R>::make(a.x, b.x, a.y, b.y));
+            bounds2.push_back(Mk4<R>::make(a.z, b.z, a.w, b.w));
+        }
+        UP(bounds2, v.item_bound2)
         UP(items, v.items) UP(bounds, v.item_bound) UP(ops, v.ops) UP(casts, v.item_casts) UP(meshes, v.item_mesh) UP(progs, v.item_prog)
         v.mesh_packet = largeMesh(L) ? 1 : 0;
         v.n_items = (int)L.items.size();

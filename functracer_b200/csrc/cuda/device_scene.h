@@ -104,6 +104,7 @@ struct DevScene {
     const int4* items;     // x = kind | CSG op << 8 | kind word of leaf a << 12 | of leaf b << 21 (kind word: leaf_meta.x & 0x1ff), y = a, z = b, w = casts_shadow
     const int2* item_prog; // CSG items: x = first op, y = op count of the general program
     const R4* item_bound;  // xyz = centre, w = (inflated radius)^2 of a conservative bounding sphere (+inf: unbounded)
+    const R4* item_bound2; // FP32: the same bounds, two neighbouring items interleaved for the packed test: (x0 x1 y0 y1) (z0 z1 w0 w1), padded to an even count
     const unsigned* item_casts;  // bit j of word w: item 32 w + j can block light (something under it has applyLighting)
     const unsigned* item_mesh;   // bit j of word w: item 32 w + j is a mesh leaf
     int mesh_packet;             // 1: mesh leaves are walked by the whole warp (render.cuh packetMesh; large meshes), 0: by each lane (intersectMesh)

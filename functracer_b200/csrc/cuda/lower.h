@@ -27,7 +27,7 @@ namespace ftb {
 constexpr int kOriginCap = 256;     // rows x items (4 KB of shared memory in FP32)
 constexpr int kOriginMinItems = 8;
 constexpr unsigned kFeatOriginTable = 0x200;
-inline bool wantsOriginTable(int n_items, int n_lights) { return n_items >= kOriginMinItems && (1 + n_lights) * n_items <= kOriginCap; }
+inline bool wantsOriginTable(int n_items, int n_lights) { return n_items >= kOriginMinItems && (1 + n_lights) * ((n_items + 1) & ~1) <= kOriginCap; }  // an origin's rows: render.cuh tabStride
 
 enum LeafKind : int32_t {
     LEAF_SPHERE = 0,

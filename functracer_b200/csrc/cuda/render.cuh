@@ -143,6 +143,33 @@ FTB_DEV R angleBetween(Vec<R> a, Vec<R> b)
 template <typename R>
 FTB_DEV Vec<R> perpendicularComponent(Vec<R> a, Vec<R> b) { Vec<R> na = normalise(a); return b - dot(b, na) * na; }  // :77-79
 
+// ---- packed FP32 (sm_100: FADD2 / FMUL2 / FFMA2) -------------------------------------------------------------------
+// Blackwell's FMA pipe takes two FP32 operations in one instruction when the operands sit in aligned register pairs
+// (PTX add / mul / fma .f32x2); a pair built from twice the same scalar costs nothing, SASS has a broadcast operand form.
+// Each half is rounded exactly like the scalar instruction.  The kernel is bounded by issue slots and dependent-issue
+// latency, not by the pipe, so the two halves of a pair are work that would otherwise be two instructions of one chain
+// after the other: the bound tests of two neighbouring items, origin and direction of a ray under the same matrix row.
+// FP32 product build only; the FP64 verification build keeps the literal scalar forms.
+typedef unsigned long long F2;  // two floats in one aligned register pair: lo = first, hi = second
+FTB_DEV F2 pk2(float lo, float hi) { return ((F2)__float_as_uint(hi) << 32) | (F2)__float_as_uint(lo); }
+FTB_DEV float lo2(F2 v) { return __uint_as_float((unsigned)v); }
+FTB_DEV float hi2(F2 v) { return __uint_as_float((unsigned)(v >> 32)); }
+FTB_DEV F2 add2(F2 a, F2 b) { F2 r; asm("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+FTB_DEV F2 sub2(F2 a, F2 b) { F2 r; asm("sub.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+FTB_DEV F2 mul2(F2 a, F2 b) { F2 r; asm("mul.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+FTB_DEV F2 fma2(F2 a, F2 b, F2 c) { F2 r; asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+FTB_DEV F2 dup2(float x) { return pk2(x, x); }
+
+// Where the packed forms are used, per variant (measured, profiles/r2aa_packed_fp32_ab.txt):
+//   the common-origin table two items per step: every FP32 variant (repeat -4.3 %, house -2.0 %, night-house -3.7 %, hollow-sphere -1.9 %,
+//   frames identical);
+//   the general bound loop two items per step: the house-family variants (on top of the table: repeat -0.7 %, house -1.1 %, night-house
+//   -1.5 %); hollow-sphere +2.8 %, moon +2.3 %, the 960-triangle mesh +3.4 % with it (their unrolled compare loops already overlap the items);
+//   origin and direction through a matrix row as one pair: the variants of the simple scenes (moon -1.3 %); it costs the CSG variants
+//   72 bytes of spills for nothing (repeat +0.7 %, house -0.3 %, hollow-sphere +0.5 %).
+template <typename R, unsigned FEAT> struct PackedBounds { static constexpr bool value = sizeof(R) == 4 && (FEAT & (FT_PAIRG | FT_CSGN)) != 0; };
+template <typename R, unsigned FEAT> struct PackedXform { static constexpr bool value = sizeof(R) == 4 && (FEAT & (FT_CUBE | FT_ROUND | FT_MESH | FT_CSG | FT_CSGN)) == 0; };
+
 template <typename R>
 struct Ray {
     Vec<R> o, d;
@@ -159,17 +186,28 @@ FTB_DEV double4 ldg4<double>(const double4* p)
 }
 
 // world -> model with the leaf's composed matrix (Transform.fs:85, matrices pre-multiplied on the host)
-template <typename R>
+template <bool PACK, typename R>
 FTB_DEV Ray<R> toModel(const DevScene<R>& S, int leaf, bool identity, const Ray<R>& r)
 {
     if (identity) return r;
     typedef typename V4<R>::type R4;
     R4 r0 = ldg4<R>(S.leaf_w2m + 3 * leaf), r1 = ldg4<R>(S.leaf_w2m + 3 * leaf + 1), r2 = ldg4<R>(S.leaf_w2m + 3 * leaf + 2);
     Ray<R> m;
-    m.o = mk<R>(r0.x * r.o.x + r0.y * r.o.y + r0.z * r.o.z + r0.w, r1.x * r.o.x + r1.y * r.o.y + r1.z * r.o.z + r1.w,
-                r2.x * r.o.x + r2.y * r.o.y + r2.z * r.o.z + r2.w);
-    m.d = mk<R>(r0.x * r.d.x + r0.y * r.d.y + r0.z * r.d.z, r1.x * r.d.x + r1.y * r.d.y + r1.z * r.d.z,
-                r2.x * r.d.x + r2.y * r.d.y + r2.z * r.d.z);
+    if constexpr (PACK) {
+        // origin and direction go through a matrix row together: (o.c, d.c) pairs against the row's broadcast elements, the
+        // translation as the origin half's first addend: 9 FFMA2 instead of 21 scalar operations (sum order w + x + y + z)
+        const F2 px = pk2(r.o.x, r.d.x), py = pk2(r.o.y, r.d.y), pz = pk2(r.o.z, r.d.z);
+        const F2 m0 = fma2(dup2(r0.z), pz, fma2(dup2(r0.y), py, fma2(dup2(r0.x), px, pk2(r0.w, 0.0f))));
+        const F2 m1 = fma2(dup2(r1.z), pz, fma2(dup2(r1.y), py, fma2(dup2(r1.x), px, pk2(r1.w, 0.0f))));
+        const F2 m2 = fma2(dup2(r2.z), pz, fma2(dup2(r2.y), py, fma2(dup2(r2.x), px, pk2(r2.w, 0.0f))));
+        m.o = mk<R>(lo2(m0), lo2(m1), lo2(m2));
+        m.d = mk<R>(hi2(m0), hi2(m1), hi2(m2));
+    } else {
+        m.o = mk<R>(r0.x * r.o.x + r0.y * r.o.y + r0.z * r.o.z + r0.w, r1.x * r.o.x + r1.y * r.o.y + r1.z * r.o.z + r1.w,
+                    r2.x * r.o.x + r2.y * r.o.y + r2.z * r.o.z + r2.w);
+        m.d = mk<R>(r0.x * r.d.x + r0.y * r.d.y + r0.z * r.d.z, r1.x * r.d.x + r1.y * r.d.y + r1.z * r.d.z,
+                    r2.x * r.d.x + r2.y * r.d.y + r2.z * r.d.z);
+    }
     return m;
 }
 
@@ -453,7 +491,7 @@ FTB_DEV void intersectLeaf(const DevScene<R>& S, int leaf, int kw, const Ray<R>&
 {
     const int kind = kw & 0xff;
     const bool identity = (kw >> 8) & 1;
-    const Ray<R> r = toModel(S, leaf, identity, wr);
+    const Ray<R> r = toModel<PackedXform<R, FEAT>::value, R>(S, leaf, identity, wr);
     cn.add(ST_LEAF0 + kind);
     if (!identity) cn.add(ST_XFORM);
     if (kind == LEAF_SPHERE) {  // Sphere.fs:11-21
@@ -873,6 +911,47 @@ template <unsigned FEAT> struct BoundUnroll { static constexpr int value = FTB_B
 template <unsigned FEAT> struct BoundUnroll { static constexpr int value = (FEAT & (FT_PAIRG | FT_CSGN | FT_MESH)) != 0 ? 1 : 4; };
 #endif
 
+// ---- the common-origin bound table (see the derivation in render_kernel's prologue) --------------------------------------
+// Layout.  FP64: one row (v.xyz, threshold) per item.  FP32: the rows of two neighbouring items interleaved,
+// (x0 x1 y0 y1) (z0 z1 -w0 -w1), so that the test of both is one chain of packed operations; an odd item count is padded
+// with a row that the candidate mask drops.  Either way an origin's rows take tabStride(n_items) R4 slots.
+template <typename R> struct TabPairs { static constexpr bool value = sizeof(R) == 4; };
+FTB_DEV int tabStride(int n_items) { return (n_items + 1) & ~1; }
+template <typename R>
+FTB_DEV bool originTableFits(const DevScene<R>& S) { return S.n_items >= kOriginMinItems && (1 + S.n_lights) * tabStride(S.n_items) <= kOriginCap; }  // = wantsOriginTable
+template <typename R>
+FTB_DEV void buildOriginTable(const DevScene<R>& S, const DevFrame<R>& F, typename V4<R>::type* origin_tab)
+{
+    typedef typename V4<R>::type R4;
+    const int n_origins = 1 + S.n_lights;
+    const int stride = tabStride(S.n_items);
+    for (int o = 0; o < n_origins; ++o) {
+        R4 org;
+        R sign = R(1);
+        if (o == 0) { org.x = F.cam_o[0]; org.y = F.cam_o[1]; org.z = F.cam_o[2]; org.w = R(0); }
+        else { org = ldg4<R>(S.light_a + (o - 1)); sign = R(-1); }
+        for (int j = threadIdx.x; j < stride; j += blockDim.x) {
+            R4 row;
+            if (j < S.n_items) {
+                const R4 bound = ldg4<R>(S.item_bound + j);
+                const Vec<R> v = mk<R>(sign * (bound.x - org.x), sign * (bound.y - org.y), sign * (bound.z - org.z));
+                const R k = dot(v, v) * R(1.0 - 8e-6) - bound.w;
+                row.x = v.x; row.y = v.y; row.z = v.z;
+                row.w = !(k > R(0)) ? -inf_<R>() : sqrt_(k);  // unbounded items (w = +inf) and origins inside the bound: always candidates
+            } else {
+                row.x = row.y = row.z = R(0); row.w = -inf_<R>();  // padding: outside the candidate mask, not counted
+            }
+            if constexpr (TabPairs<R>::value) {
+                R* t = reinterpret_cast<R*>(origin_tab + o * stride + (j & ~1)) + (j & 1);
+                t[0] = row.x; t[2] = row.y; t[4] = row.z; t[6] = -row.w;
+            } else {
+                origin_tab[o * stride + j] = row;
+            }
+        }
+    }
+    __syncthreads();
+}
+
 template <typename R>
 struct HitInfo {
     R t;
@@ -891,6 +970,7 @@ FTB_DEV HitInfo<R> traceScene(const DevScene<R>& S, const Ray<R>& wr, R limit, b
 {
     typedef typename V4<R>::type R4;
     constexpr int kUnroll = BoundUnroll<FEAT>::value;  // (#pragma unroll takes constants, not macros)
+    constexpr int kPairUnroll = kUnroll > 1 ? kUnroll / 2 : 1;
     RaySink<R, (FEAT & FT_MESH) != 0> best;
     best.limit = limit; best.id = -1; best.sub = 0; best.any = any; best.cur = 0; best.overflow = false;
     int bestItem = -1;  // mesh variants: the item of the current winner (tie rule of meshHit)
@@ -907,16 +987,46 @@ FTB_DEV HitInfo<R> traceScene(const DevScene<R>& S, const Ray<R>& wr, R limit, b
             // candidate <=> !(b < w) <=> the sign bit of b - w is clear (a NaN is the canonical, positive one; w = -inf gives +inf):
             // the items are walked from the last to the first and each sign is shifted into the mask by one funnel shift.
             unsigned out = 0;
+            if constexpr (TabPairs<R>::value) {  // two items per step: (x0 x1 y0 y1) (z0 z1 -w0 -w1), one chain of packed operations
+                const F2 dx2 = dup2(du.x), dy2 = dup2(du.y), dz2 = dup2(du.z), sl2 = dup2(tabSlack);
+#pragma unroll kPairUnroll
+                for (int j = ((n + 1) & ~1) - 2; j >= 0; j -= 2) {
+                    const R4 e0 = tab[base + j], e1 = tab[base + j + 1];
+                    const F2 bw = fma2(pk2(e0.x, e0.y), dx2, fma2(pk2(e0.z, e0.w), dy2, fma2(pk2(e1.x, e1.y), dz2, add2(sl2, pk2(e1.z, e1.w)))));
+                    cn.add(ST_BOUND_FAST, (e1.z < inf_<R>() ? 1u : 0u) + (e1.w < inf_<R>() ? 1u : 0u));
+                    out = __funnelshift_l(signWord(hi2(bw)), out, 1);
+                    out = __funnelshift_l(signWord(lo2(bw)), out, 1);
+                }
+            } else {
 #pragma unroll kUnroll
-            for (int j = n - 1; j >= 0; --j) {
-                const R4 e = tab[base + j];  // xyz = centre - origin (origin - centre for a light: the ray points AT it), w = threshold
-                const R bw = e.x * du.x + (e.y * du.y + (e.z * du.z + (tabSlack - e.w)));
-                cn.add(ST_BOUND_FAST, e.w > -inf_<R>() ? 1u : 0u);
-                out = __funnelshift_l(signWord(bw), out, 1);
+                for (int j = n - 1; j >= 0; --j) {
+                    const R4 e = tab[base + j];  // xyz = centre - origin (origin - centre for a light: the ray points AT it), w = threshold
+                    const R bw = e.x * du.x + (e.y * du.y + (e.z * du.z + (tabSlack - e.w)));
+                    cn.add(ST_BOUND_FAST, e.w > -inf_<R>() ? 1u : 0u);
+                    out = __funnelshift_l(signWord(bw), out, 1);
+                }
             }
             cand = ~out & (n >= 32 ? 0xffffffffu : ((1u << n) - 1u));
         } else {
-            if constexpr (BoundSigns<FEAT>::value) {
+            if constexpr (PackedBounds<R, FEAT>::value) {  // two items per step, the same test in packed operations
+                const F2 nox = dup2(-wr.o.x), noy = dup2(-wr.o.y), noz = dup2(-wr.o.z);
+                const F2 dx2 = dup2(du.x), dy2 = dup2(du.y), dz2 = dup2(du.z);
+                unsigned out = 0;
+#pragma unroll kPairUnroll
+                for (int j = ((n + 1) & ~1) - 2; j >= 0; j -= 2) {
+                    const R4 e0 = ldg4<R>(S.item_bound2 + base + j), e1 = ldg4<R>(S.item_bound2 + base + j + 1);  // (x0 x1 y0 y1) (z0 z1 w0 w1)
+                    const F2 ocx = add2(pk2(e0.x, e0.y), nox), ocy = add2(pk2(e0.z, e0.w), noy), ocz = add2(pk2(e1.x, e1.y), noz);
+                    const F2 w = pk2(e1.z, e1.w);
+                    const F2 b = fma2(ocz, dz2, fma2(ocy, dy2, mul2(ocx, dx2)));
+                    const F2 oc2 = fma2(ocz, ocz, fma2(ocy, ocy, mul2(ocx, ocx)));
+                    const F2 miss = fma2(b, b, sub2(fma2(dup2(1e-6f), oc2, w), oc2));  // (w + 1e-6 oc2) - oc2 + b^2 < 0: the line misses the bound
+                    const F2 outside = sub2(w, oc2);                                       // < 0 and b < 0: entirely behind the origin
+                    cn.add(ST_BOUND_TESTS, (e1.z < inf_<R>() ? 1u : 0u) + (e1.w < inf_<R>() ? 1u : 0u));
+                    out = __funnelshift_l(signWord(hi2(miss)) | (signWord(hi2(b)) & signWord(hi2(outside))), out, 1);
+                    out = __funnelshift_l(signWord(lo2(miss)) | (signWord(lo2(b)) & signWord(lo2(outside))), out, 1);
+                }
+                cand = ~out & (n >= 32 ? 0xffffffffu : ((1u << n) - 1u));
+            } else if constexpr (BoundSigns<FEAT>::value) {
                 unsigned out = 0;
 #pragma unroll kUnroll
                 for (int j = n - 1; j >= 0; --j) {
@@ -1005,7 +1115,7 @@ FTB_DEV HitInfo<R> traceScene(const DevScene<R>& S, const Ray<R>& wr, R limit, b
                 const int leaf = __ldg(S.items + it).y;
                 const int4 meta = __ldg(S.leaf_meta + leaf);
                 const bool want = ((meshCand >> j) & 1u) && !(any && best.found());
-                const Ray<R> r = toModel(S, leaf, (meta.x >> 8) & 1, wr);
+                const Ray<R> r = toModel<PackedXform<R, FEAT>::value, R>(S, leaf, (meta.x >> 8) & 1, wr);
                 if (want) { cn.add(ST_LEAF0 + LEAF_MESH); if (!((meta.x >> 8) & 1)) cn.add(ST_XFORM); }
                 R bt; int btri;
                 packetMesh<R, STATS>(S, __ldg(S.mesh_root + meta.w), r, best.limit, any, want, tracing, wstack, bt, btri, cn);
@@ -1096,7 +1206,7 @@ FTB_DEV Fragment<R> finalise(const DevScene<R>& S, const Ray<R>& wr, const HitIn
     const int4 meta = __ldg(S.leaf_meta + h.leaf);
     const int kind = meta.x & 0xff;
     const bool identity = (meta.x >> 8) & 1;
-    const Ray<R> r = toModel(S, h.leaf, identity, wr);
+    const Ray<R> r = toModel<PackedXform<R, FEAT>::value, R>(S, h.leaf, identity, wr);
     const Vec<R> pm = mk<R>(r.o.x + h.t * r.d.x, r.o.y + h.t * r.d.y, r.o.z + h.t * r.d.z);
     Vec<R> nm = mk<R>(R(0), R(1), R(0));
     R u = R(0), v = R(0);
@@ -1368,27 +1478,9 @@ __global__ void __launch_bounds__(kBlockThreads, MinBlocks<FEAT>::value) render_
     // maximum over |oc|): adding sqrt(g^2 / 6e-6) = 410 g to b covers it for every item, i.e. 4.1e-5 |camera| resp.
     // 7e-5 tmax.  The per-ray slack actually added is 2e-4 |camera| for primary rays and 4e-4 tmax for shadow rays (5x).
     // -inf = always a candidate (unbounded, or the origin inside the bound).
-    const int n_origins = 1 + S.n_lights;
-    const bool fastBounds = kTable && S.n_items >= kOriginMinItems && n_origins * S.n_items <= kOriginCap;  // = wantsOriginTable
+    const bool fastBounds = kTable && originTableFits(S);
     const bool fastPrimary = fastBounds && F.mode == 0 && !((FEAT & FT_RNG) != 0 && F.has_focus);
-    if (fastBounds) {
-        for (int o = 0; o < n_origins; ++o) {
-            R4 org;
-            R sign = R(1);
-            if (o == 0) { org.x = F.cam_o[0]; org.y = F.cam_o[1]; org.z = F.cam_o[2]; org.w = R(0); }
-            else { org = ldg4<R>(S.light_a + (o - 1)); sign = R(-1); }
-            for (int j = threadIdx.x; j < S.n_items; j += kBlockThreads) {
-                const R4 bound = ldg4<R>(S.item_bound + j);
-                const Vec<R> v = mk<R>(sign * (bound.x - org.x), sign * (bound.y - org.y), sign * (bound.z - org.z));
-                const R k = dot(v, v) * R(1.0 - 8e-6) - bound.w;
-                R4 row;
-                row.x = v.x; row.y = v.y; row.z = v.z;
-                row.w = !(k > R(0)) ? -inf_<R>() : sqrt_(k);  // unbounded items (w = +inf) and origins inside the bound: always candidates
-                origin_tab[o * S.n_items + j] = row;
-            }
-        }
-        __syncthreads();
-    }
+    if (fastBounds) buildOriginTable<R>(S, F, origin_tab);
     bool overflow = false;
 
     // warp-uniform cursors: the pixel block (or 32 rays) taken from the per-GPU queue, and the unit being dealt from it
@@ -1558,7 +1650,7 @@ __global__ void __launch_bounds__(kBlockThreads, MinBlocks<FEAT>::value) render_
             if (f.planarLeaf >= 0 && (phase == PH_NEAREST ? limit < F.recursion_limit : dot(ray.d, f.n) >= R(0))) skipLeaf = f.planarLeaf;
         }
         const HitInfo<R> h = traceScene<R, FEAT, STATS>(S, tr, phase == PH_NEAREST ? inf_<R>() : tmax, phase == PH_SHADOW, skipLeaf,
-                                                        tabled ? origin_tab + (phase == PH_NEAREST ? 0 : 1 + li) * S.n_items : nullptr,
+                                                        tabled ? origin_tab + (phase == PH_NEAREST ? 0 : 1 + li) * tabStride(S.n_items) : nullptr,
                                                         phase == PH_NEAREST ? F.primary_slack : R(4e-4) * tmax,
                                                         overflow, cn, tracing, &mesh_stack[MeshWalks<FEAT>::kPacket ? wib : 0][0]);
 

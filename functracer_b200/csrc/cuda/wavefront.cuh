@@ -82,28 +82,8 @@ FTB_DEV bool wfLocate(const DevFrame<R>& F, const WfState<R>& W, long long pid, 
 template <typename R, unsigned FEAT>
 FTB_DEV bool wfOriginTable(const DevScene<R>& S, const DevFrame<R>& F, typename V4<R>::type* origin_tab)
 {
-    typedef typename V4<R>::type R4;
-    constexpr bool kTable = (FEAT & FT_TABLE) != 0;
-    const int n_origins = 1 + S.n_lights;
-    const bool fastBounds = kTable && S.n_items >= kOriginMinItems && n_origins * S.n_items <= kOriginCap;
-    if (fastBounds) {
-        for (int o = 0; o < n_origins; ++o) {
-            R4 org;
-            R sign = R(1);
-            if (o == 0) { org.x = F.cam_o[0]; org.y = F.cam_o[1]; org.z = F.cam_o[2]; org.w = R(0); }
-            else { org = ldg4<R>(S.light_a + (o - 1)); sign = R(-1); }
-            for (int j = threadIdx.x; j < S.n_items; j += blockDim.x) {
-                const R4 bound = ldg4<R>(S.item_bound + j);
-                const Vec<R> v = mk<R>(sign * (bound.x - org.x), sign * (bound.y - org.y), sign * (bound.z - org.z));
-                const R k = dot(v, v) * R(1.0 - 8e-6) - bound.w;
-                R4 row;
-                row.x = v.x; row.y = v.y; row.z = v.z;
-                row.w = !(k > R(0)) ? -inf_<R>() : sqrt_(k);
-                origin_tab[o * S.n_items + j] = row;
-            }
-        }
-        __syncthreads();
-    }
+    const bool fastBounds = (FEAT & FT_TABLE) != 0 && originTableFits(S);
+    if (fastBounds) buildOriginTable<R>(S, F, origin_tab);
     return fastBounds;
 }
 
@@ -281,7 +261,7 @@ __global__ void __launch_bounds__(kWfThreads) wf_shadow(const __grid_constant__ 
             Ray<R> r;
             r.o = mk<R>(so.x, so.y, so.z); r.d = mk<R>(sd.x, sd.y, sd.z);
             const int li = info & 0xff, skip = ((info >> 16) & 0x7fff) - 1;
-            const HitInfo<R> h = traceScene<R, FEAT, false>(S, r, so.w, true, skip, tabled ? origin_tab + (1 + li) * S.n_items : nullptr, R(4e-4) * so.w, overflow, cn, 0xffffffffu, nullptr);
+            const HitInfo<R> h = traceScene<R, FEAT, false>(S, r, so.w, true, skip, tabled ? origin_tab + (1 + li) * tabStride(S.n_items) : nullptr, R(4e-4) * so.w, overflow, cn, 0xffffffffu, nullptr);
             W.sres[j] = h.leaf >= 0 ? 1 : 0;
         }
     }
