@@ -409,18 +409,15 @@ int uploadScene(const ftb_scene& sc, SceneStorage<R>& st)
         UP(texels, v.texels) UP(ii, v.img_i)
     }
     {
-        std::vector<int> roots(L.mesh_root.begin(), L.mesh_root.end()); std::vector<int2> links; std::vector<R4> box, btris, tris;
+        std::vector<int> roots(L.mesh_root.begin(), L.mesh_root.end()); std::vector<R4> box, btris, tris;
         for (const BvhNode& n : L.bvh_nodes) {
-            if (sizeof(R) == 4) {
-                box.push_back(Mk4<R>::make(n.lo[0][0], n.lo[0][1], n.lo[0][2], n.hi[0][0]));
-                box.push_back(Mk4<R>::make(n.hi[0][1], n.hi[0][2], n.lo[1][0], n.lo[1][1]));
-                box.push_back(Mk4<R>::make(n.lo[1][2], n.hi[1][0], n.hi[1][1], n.hi[1][2]));
-            } else {
-                box.push_back(Mk4<R>::make(n.dlo[0][0], n.dlo[0][1], n.dlo[0][2], n.dhi[0][0]));
-                box.push_back(Mk4<R>::make(n.dhi[0][1], n.dhi[0][2], n.dlo[1][0], n.dlo[1][1]));
-                box.push_back(Mk4<R>::make(n.dlo[1][2], n.dhi[1][0], n.dhi[1][1], n.dhi[1][2]));
+            for (int k = 0; k < 3; ++k) {  // one row per axis: (L.lo, R.lo, L.hi, R.hi)
+                if (sizeof(R) == 4) box.push_back(Mk4<R>::make(n.lo[0][k], n.lo[1][k], n.hi[0][k], n.hi[1][k]));
+                else box.push_back(Mk4<R>::make(n.dlo[0][k], n.dlo[1][k], n.dhi[0][k], n.dhi[1][k]));
             }
-            links.push_back(make_int2(n.child[0], n.child[1]));
+            R4 lk = Mk4<R>::make(n.child[0], n.child[1], 0, 0);  // the links in the record's fourth row: FP64 as values, FP32 as bits
+            if (sizeof(R) == 4) { std::memcpy(&lk.x, &n.child[0], 4); std::memcpy(&lk.y, &n.child[1], 4); }
+            box.push_back(lk);
         }
         const size_t nt = sc.triangles.size() / 9;
         auto pushTri = [&](std::vector<R4>& dst, size_t t, double w0, double w1) {  // v0, e1 = v1 - v0, e2 = v2 - v0 (Triangle.fs:45-46), differences taken in double
@@ -433,7 +430,7 @@ int uploadScene(const ftb_scene& sc, SceneStorage<R>& st)
         // slot ids ride in the w components as reals: exact up to 2^24 in float
         if (sizeof(R) == 4 && (L.bvh_tri.size() >= (1u << 24) || nt >= (1u << 24))) { st.release(); return fail(FTB_ERR_UNSUPPORTED, "more than 16M mesh triangles"); }
         for (size_t k = 0; k < L.bvh_tri.size(); ++k) pushTri(btris, (size_t)L.bvh_tri[k], (double)L.bvh_seq[k], (double)L.bvh_tri[k]);
-        UP(roots, v.mesh_root) UP(box, v.bvh_box) UP(links, v.bvh_links) UP(btris, v.bvh_tris) UP(tris, v.tris)
+        UP(roots, v.mesh_root) UP(box, v.bvh_node) UP(btris, v.bvh_tris) UP(tris, v.tris)
     }
     {
         std::vector<int2> li; std::vector<R4> la, lb, lc;

@@ -124,8 +124,8 @@ struct DevScene {
     const int4* img_i;  // x = first texel, y = width, z = height
     // meshes: the device's own BVH over each mesh's triangles (lower.h BvhNode)
     const int* mesh_root;    // per mesh: root link (>= 0 node, < 0 ~((first << 3) | count))
-    const R4* bvh_box;       // 3 per node: (L.lo.xyz, L.hi.x) (L.hi.yz, R.lo.xy) (R.lo.z, R.hi.xyz)
-    const int2* bvh_links;   // per node: child links
+    const R4* bvh_node;      // 4 per node (64 bytes): one row per axis, (L.lo, R.lo, L.hi, R.hi) of x, of y, of z (render.cuh boxEntry2: both children's
+                             // slabs as packed pairs), then (child link L, child link R, -, -) as bits (FP32) or values (FP64)
     const R4* bvh_tris;      // 3 per slot: (v0, seq) (e1, triangle index) (e2, -); the ints stored as reals
     const R4* tris;          // 3 per scene triangle: v0, e1 = v1 - v0, e2 = v2 - v0 (LEAF_TRIANGLE, normals)
     // lights
