@@ -25,7 +25,7 @@ namespace ftb {
 // The common-origin bound table (render.cuh) is used when the item list is long enough to matter and the table fits;
 // such scenes carry the feature bit 0x200 (device_scene.h FT_TABLE).
 constexpr int kOriginCap = 256;     // rows x items (4 KB of shared memory in FP32)
-constexpr int kOriginMinItems = 8;
+constexpr int kOriginMinItems = 8;  // measured again with the packed table walk: at 4 items (the moon scene) the table costs +4.2 %, sample +8 % (profiles/r2ae_table_min4_ab.txt)
 constexpr unsigned kFeatOriginTable = 0x200;
 inline bool wantsOriginTable(int n_items, int n_lights) { return n_items >= kOriginMinItems && (1 + n_lights) * ((n_items + 1) & ~1) <= kOriginCap; }  // an origin's rows: render.cuh tabStride
 

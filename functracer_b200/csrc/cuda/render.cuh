@@ -1325,14 +1325,33 @@ template <typename R>
 FTB_DEV Vec<R> roughDiffuse(const Fragment<R>& f, Vec<R> lightDir, Vec<R> viewD)  // Shading.fs:50-63
 {
     R roughness = f.roughness * f.roughness;
-    R rayAngle = angleBetween(f.n, -viewD);
-    R lightAngle = angleBetween(f.n, -lightDir);
-    R alpha = fsmax(rayAngle, lightAngle);
-    R beta = fsmin(rayAngle, lightAngle);
     R A = R(1) - R(0.5) * roughness / (roughness + R(0.33));
     R B = R(0.45) * roughness / (roughness + R(0.09));
     Vec<R> tangentLight = normalise(perpendicularComponent(f.n, -lightDir));
     Vec<R> tangentRay = normalise(perpendicularComponent(f.n, -viewD));
+    if constexpr (sizeof(R) == 4) {
+        // FP32 product build: the model only wants cos(lightAngle), sin(alpha) and tan(beta) of the two angles, so the angles themselves
+        // (two acos, then cos / sin / tan of their results: ~90 instructions and four more roundings) are never formed:
+        // cos(lightAngle) is the clamped dot product angleBetween takes the acos of; alpha, the larger angle, has the smaller cosine
+        // ca, beta the larger one cb; sin(alpha) = sqrt((1 - ca)(1 + ca)) >= 0 on [0, pi], tan(beta) = sqrt((1 - cb)(1 + cb)) / cb.
+        // In real arithmetic the same value as the literal form (which the FP64 verification build keeps); in FP32 closer to it
+        // (moon -0.9 %, 127 of 133 M frame bytes move by one step; profiles/r2ad_rough_trig_ab.txt).
+        // fsmin / fsmax keep F#'s NaN propagation; |cb| is kept off zero so that the grazing case stays finite like tanf(fl(pi / 2)).
+        const Vec<R> nn = normalise(f.n);
+        const R cr = min_(R(1), max_(R(-1), dot(nn, normalise(-viewD))));
+        const R cl = min_(R(1), max_(R(-1), dot(nn, normalise(-lightDir))));
+        const R ca = fsmin(cr, cl);
+        R cb = fsmax(cr, cl);
+        if (abs_(cb) < R(4e-8)) cb = cb < R(0) ? R(-4e-8) : R(4e-8);
+        const R sinAlpha = sqrt_((R(1) - ca) * (R(1) + ca));
+        const R tanBeta = sqrt_((R(1) - cb) * (R(1) + cb)) / cb;
+        const R intensity = cl * (A + (B * fsmax(R(0), dot(tangentLight, tangentRay)) * sinAlpha * tanBeta));
+        return intensity * f.colour;
+    }
+    R rayAngle = angleBetween(f.n, -viewD);
+    R lightAngle = angleBetween(f.n, -lightDir);
+    R alpha = fsmax(rayAngle, lightAngle);
+    R beta = fsmin(rayAngle, lightAngle);
     R intensity = cos_(lightAngle) * (A + (B * fsmax(R(0), dot(tangentLight, tangentRay)) * sin_(alpha) * tan_(beta)));
     return intensity * f.colour;
 }
