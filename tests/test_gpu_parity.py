@@ -305,6 +305,23 @@ def test_bound_table_cannot_change_a_pixel():
     assert prim_diff <= 3e-4 and rgb_diff <= 3e-4  # the smallest shadow in the picture is ~20 pixels, most are hundreds
 
 
+@pytest.mark.parametrize("n_spheres", [40, 63, 84])
+def test_bound_table_batches_and_padding(n_spheres):
+    """The FP32 kernels walk the common-origin table two items per step (the rows of neighbouring items are interleaved, an odd
+    item count is padded) in batches of 32 items: 41 items = two batches with a padded last pair, 64 = exactly two full batches,
+    85 = three batches, odd, the largest count whose two origins (camera + one point light) still fit the table.  Every sphere
+    is visible and lit, so a pair tested against the wrong row or a dropped last item costs whole objects or shadows."""
+    objs = ["(%s plane)" % scenes._mat((1, 1, 1))]
+    for i in range(n_spheres):
+        objs.append("(%s (translate (%g,0.45,%g) (scale 0.45 sphere)))" % (scenes._mat((0.3 + 0.05 * (i % 12), 0.9 - 0.07 * (i // 12), 0.4), 0, 10), -6.0 + 1.1 * (i % 12), 1.2 * (i // 12)))
+    cam = "camera pos (0,7,-9) lookat (0,0,3) up (0,1,0) fov 55 ratio 1"
+    text = scenes._options(cam, (192, 144), 1) + "\n".join(objs) + "\n\npositional pos (2,9,-3) falloff (1,0.01,0.002) colour (1,1,1)\n"
+    for prec in (abi.PRECISION_FP64_VERIFY, abi.PRECISION_FP32):
+        ref, got = both(text, precision=prec)
+        assert len(np.unique(ref["prim"])) >= n_spheres  # the plane and (nearly) every sphere own pixels of the frame
+        check(ref, got, prec, "table-%d" % (n_spheres + 1))
+
+
 @pytest.mark.parametrize("w,h,sampling", [(8, 40, abi.SAMPLING_JITTER), (16, 40, abi.SAMPLING_JITTER), (15, 40, abi.SAMPLING_CORNER), (3, 70, abi.SAMPLING_JITTER)])
 def test_frames_one_tile_wide(w, h, sampling):
     """A sample grid of at most 16 columns has tiles_x == 1: the tile -> (row, column) split of the work queue must not use
