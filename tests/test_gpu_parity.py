@@ -40,8 +40,9 @@ def check(ref, got, precision, name, id_frac=None, within=None):
     # which of the mismatching samples are the documented kind: the kernel's answer is a primitive the
     # oracle's own id map shows within one pixel (a silhouette / tie, where the last bits of t decide), oracle/parity.py
     gp, rp = np.asarray(got["prim"]), np.asarray(ref["prim"])
-    h, w = np.asarray(ref["rgb"]).shape[:2]
-    if mism > 0 and gp.size == rp.size and gp.size % (h * w) == 0:  # jittered sampling: sample index = (y * W + x) * spp + s
+    rgb = np.asarray(ref["rgb"])
+    h, w = (rgb.shape[0], rgb.shape[1]) if rgb.ndim == 3 else (0, 0)  # frames only (explicit-ray results are [n, 3])
+    if mism > 0 and h * w > 0 and gp.size == rp.size and gp.size % (h * w) == 0:  # jittered sampling: sample index = (y * W + x) * spp + s
         c = parity.compare_window(ref["rgb"], rp.reshape(h, w, -1), got["rgb"], gp.reshape(h, w, -1))
         print("    %d mismatching samples of %d: %d on a silhouette of the two ids, %d not" %
               (c["prim_mismatch"], c["samples"], c["prim_mismatch"] - c["prim_unexplained"], c["prim_unexplained"]))
