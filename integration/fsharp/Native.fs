@@ -1,4 +1,5 @@
-/// P/Invoke face of libfunctracer_b200.so — field for field include/functracer_b200.h (ABI version 3).
+/// P/Invoke face of libfunctracer_b200.so — field for field include/functracer_b200.h (ABI version 4;
+/// tests/test_fsharp_binding.py lays these structs out by the CLR's rules and compares them with the header's).
 /// Blittable structs, Sequential layout (the C compiler's natural alignment: 4-byte ints, 8-byte doubles / pointers).
 module Native
 
@@ -147,6 +148,8 @@ type FtbRenderParams =
 
 [<Literal>]
 let Lib = "functracer_b200"
+[<Literal>]
+let AbiVersion = 4
 
 [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
 extern int ftb_abi_version()
@@ -165,3 +168,5 @@ extern int ftb_shade_rays(nativeint scene, nativeint raysOD, int64 n, FtbRenderP
 
 let lastError () = Marshal.PtrToStringAnsi (ftb_last_error ())
 let check rc = if rc <> 0 then failwithf "functracer_b200 status %d: %s" rc (lastError ())
+/// the structs above are only valid against the ABI they were written for
+let checkAbi () = if ftb_abi_version () <> AbiVersion then failwithf "libfunctracer_b200 has ABI %d, this binding is for %d" (ftb_abi_version ()) AbiVersion

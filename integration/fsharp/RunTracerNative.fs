@@ -22,6 +22,7 @@ let run (timer: Diagnostics.Stopwatch) (options: Scene.SceneOptions) (sampling: 
             n, 0, pattern |> List.collect (fun (Jitter.JitterOffset (x, y)) -> [x; y]) |> List.toArray
         | Corner -> 1, 1, [| 0.0; 0.0 |]
     eprintfn "Generated rays: %ims" timer.ElapsedMilliseconds
+    checkAbi ()
     use flat = new SceneFlatten.Flattened (scene, options.camera)
     let mutable desc = flat.desc
     let mutable camera = flat.camera
