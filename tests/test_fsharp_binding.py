@@ -112,3 +112,32 @@ def test_shim_targets_this_abi_and_the_rgba8_path():
     assert "checkAbi ()" in run                                       # refuses a library of another ABI before passing structs
     assert "recursionLimit = 8" in run                                # Shading.fs:142
     assert "GCHandleType.Pinned" in run                               # the caller's buffer is ordinary pageable memory
+
+
+def test_flattener_emits_the_headers_enum_values():
+    """SceneFlatten.fs writes node / primitive / texture / light kinds as literals; they must be the header's enum values
+    (mirrored in abi.py, which tests/test_abi.py::test_enums_match_header pins to the header)."""
+    text = open(os.path.join(FS, "SceneFlatten.fs")).read()
+    # primKind: `| Name [_] -> k`
+    body = text[text.index("let private primKind = function"):text.index("type Tables")]
+    prim = {n.lower(): int(k) for n, k in re.findall(r"\|\s*(\w+)(?:\s+_)?\s*->\s*(\d+)", body)}
+    assert prim == {n.lower(): i for i, n in enumerate(abi.PRIM_NAMES)}
+    # node kinds: the first argument of the FtbNode constructed under each SceneGraph case
+    node = text[text.index("let rec private addNode"):text.index("let private addLight")]
+    want = {"Primitive": abi.NODE_PRIMITIVE, "Transform": abi.NODE_TRANSFORM, "Material": abi.NODE_MATERIAL, "Texture": abi.NODE_TEXTURE,
+            "HueShift": abi.NODE_HUESHIFT, "IgnoreLight": abi.NODE_IGNORELIGHT, "Group": abi.NODE_GROUP, "Union": abi.NODE_UNION,
+            "Intersect": abi.NODE_INTERSECT, "Subtract": abi.NODE_SUBTRACT, "Exclude": abi.NODE_EXCLUDE}
+    for case, kind in want.items():
+        at = re.search(r"\|\s*%s\b" % case, node)  # the case's arm, then the first node it emits
+        m = at and re.search(r"FtbNode \((\d+),", node[at.end():])
+        assert m and int(m.group(1)) == kind, (case, m and m.group(1))
+    tex = text[text.index("let rec private addTexture"):text.index("let rec private addNode")]
+    for case, kind in (("Image", abi.TEX_IMAGE), ("Grid", abi.TEX_GRID), ("Scale", abi.TEX_SCALE), ("Rotate", abi.TEX_ROTATE)):
+        at = re.search(r"\|[^\n]*\b%s\b[^\n]*->" % case, tex)
+        m = at and re.search(r"FtbTexture \(kind = (\d+)", tex[at.end():])
+        assert m and int(m.group(1)) == kind, case
+    light = text[text.index("let private addLight"):text.index("type Flattened")]
+    for case, kind in (("Directional", abi.LIGHT_DIRECTIONAL), ("SoftDirectional", abi.LIGHT_SOFT_DIRECTIONAL), ("Point", abi.LIGHT_POINT)):
+        at = re.search(r"\|\s*%s \(" % case, light)
+        m = at and re.search(r"FtbLight \(kind = (\d+)", light[at.end():])
+        assert m and int(m.group(1)) == kind, case
