@@ -22,6 +22,7 @@ CSRC = os.path.join(ROOT, "functracer_b200", "csrc")
 
 PROBE = r"""
 #include "%(csrc)s/cuda/lower.h"
+#include <algorithm>
 #include <cstring>
 extern "C" int ftb_probe_lower(const ftb_scene_desc* d, unsigned* features, int* counts, char* err, int errlen)
 {
@@ -59,6 +60,76 @@ extern "C" int ftb_probe_bounds(const ftb_scene_desc* d, int max_items, double* 
     }
     return 0;
 }
+// The host-built mesh index (buildMeshIndexHost, the builder of meshes below 32 768 triangles and the device build's fallback):
+// checks, for every mesh a bspMesh primitive uses, that the walk from its root reaches every triangle slot exactly once, that
+// each child box (FP32, rounded outward, and FP64) contains every vertex below it, that leaves hold 1..7 slots, that the depth
+// fits the traversal stack, and that `seq` ranks the mesh's triangles in BspMesh.intersect's right-before-left order.
+// Returns the number of triangle slots checked, or a negative code naming the first violation.
+#include <cfloat>
+#include <functional>
+extern "C" long ftb_probe_mesh_index(const ftb_scene_desc* d, int* depth_out)
+{
+    ftb::Lowered L;
+    std::string e;
+    if (ftb::lower_scene(*d, L, e, true) != 0) return -1;
+    std::vector<std::vector<int32_t>> order;
+    ftb::enumerateMeshes(*d, L, order);
+    std::vector<int> seen(L.bvh_tri.size(), 0);
+    long checked = 0;
+    int maxDepth = 0;
+    for (size_t m = 0; m < L.mesh_root.size(); ++m) {
+        if (!L.mesh_used[m]) continue;
+        std::vector<std::pair<int32_t, int32_t>> bySeq;  // (seq, triangle)
+        // returns the box of everything below `link` in double
+        std::function<int(int32_t, int, double*, double*)> walk = [&](int32_t link, int depth, double* lo, double* hi) -> int {
+            if (depth > maxDepth) maxDepth = depth;
+            for (int k = 0; k < 3; ++k) { lo[k] = DBL_MAX; hi[k] = -DBL_MAX; }
+            if (link < 0) {
+                const int code = ~link, first = code >> 3, count = code & 7;
+                if (count < 1 || first < 0 || (size_t)(first + count) > L.bvh_tri.size()) return -10;
+                for (int s = first; s < first + count; ++s) {
+                    if (seen[(size_t)s]++) return -11;
+                    const int32_t tri = L.bvh_tri[(size_t)s];
+                    if (tri < 0 || tri >= d->n_triangles) return -12;
+                    bySeq.push_back({L.bvh_seq[(size_t)s], tri});
+                    for (int v = 0; v < 3; ++v)
+                        for (int k = 0; k < 3; ++k) {
+                            const double x = d->triangles[9 * (size_t)tri + 3 * v + k];
+                            if (x < lo[k]) lo[k] = x;
+                            if (x > hi[k]) hi[k] = x;
+                        }
+                    ++checked;
+                }
+                return 0;
+            }
+            if ((size_t)link >= L.bvh_nodes.size()) return -13;
+            const ftb::BvhNode& n = L.bvh_nodes[(size_t)link];
+            for (int c = 0; c < 2; ++c) {
+                double clo[3], chi[3];
+                const int rc = walk(n.child[c], depth + 1, clo, chi);
+                if (rc) return rc;
+                for (int k = 0; k < 3; ++k) {
+                    if (!((double)n.lo[c][k] <= clo[k] && (double)n.hi[c][k] >= chi[k])) return -14;  // the FP32 box must contain its subtree
+                    if (!(n.dlo[c][k] <= clo[k] && n.dhi[c][k] >= chi[k])) return -15;                // and so must the FP64 one
+                    if (clo[k] < lo[k]) lo[k] = clo[k];
+                    if (chi[k] > hi[k]) hi[k] = chi[k];
+                }
+            }
+            return 0;
+        };
+        double lo[3], hi[3];
+        const int rc = walk(L.mesh_root[m], 0, lo, hi);
+        if (rc) return rc;
+        std::sort(bySeq.begin(), bySeq.end());
+        if (bySeq.size() != order[m].size()) return -16;
+        for (size_t i = 0; i < bySeq.size(); ++i)
+            if (bySeq[i].first != (int32_t)i || bySeq[i].second != order[m][i]) return -17;  // seq = rank in the reference's enumeration
+    }
+    for (size_t s = 0; s < seen.size(); ++s) if (seen[s] != 1) return -18;
+    if (maxDepth != 0 && maxDepth > L.max_bvh_depth + 1) return -19;
+    *depth_out = L.max_bvh_depth;
+    return checked;
+}
 """
 
 FT_TABLE, FT_RNG, FT_MESHPK, FT_ALL = 0x200, 0x40, 0x800, 0xfff
@@ -76,6 +147,8 @@ def probe(tmp_path_factory):
     lib.ftb_probe_lower.restype = C.c_int
     lib.ftb_probe_bounds.argtypes = [C.POINTER(abi.SceneDesc), C.c_int, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.ftb_probe_bounds.restype = C.c_int
+    lib.ftb_probe_mesh_index.argtypes = [C.POINTER(abi.SceneDesc), C.POINTER(C.c_int)]
+    lib.ftb_probe_mesh_index.restype = C.c_long
     return lib
 
 
@@ -236,3 +309,18 @@ def test_bundled_scenes_crossings_lie_inside_their_items_bounds(probe, name):
             checked += 1
     print("%s: %d items, %d crossings checked" % (name, bounds.shape[0], checked))
     assert checked > 0 or name == "cfg1-sample"
+
+
+@pytest.mark.parametrize("name,kw", [("cfg4-bunny", {}), ("cfg4-bunny-d12", {}), ("cfg4-bunny", dict(depth=3, mesh="bunny_tiny.ply")),
+                                     ("cfg4-bunny", dict(depth=4, mesh="bunny_res4.ply"))])
+def test_host_mesh_index_invariants(probe, name, kw):
+    """The host build of the device's mesh index (lower.cpp buildMeshIndexHost): every clipped triangle in exactly one leaf, boxes
+    that contain their subtrees in both precisions, leaves within the slot-count encoding, a depth the 64-entry traversal stack
+    can hold, and `seq` = the triangle's rank in BspMesh.intersect's right-before-left enumeration (BspMesh.fs:67-76) - the
+    tie-break that makes the BVH's answer the reference's."""
+    sc = frontend.ParsedScene(scenes.config_text(name, res=(32, 24), spp=1, **kw), scenes.asset_dir())
+    depth = C.c_int(0)
+    n = probe.ftb_probe_mesh_index(sc.desc_ptr, C.byref(depth))
+    print("%s %s: %d triangle slots, index depth %d" % (name, kw, n, depth.value))
+    assert n > 0, "violation %d" % n
+    assert depth.value + 2 <= 64  # api.cu refuses deeper indices (kBspStack)
