@@ -167,3 +167,54 @@ def test_origin_inside_or_unbounded_is_always_a_candidate():
     assert np.isneginf(s).all()
     du = _unit32(_rand_dirs(rng, n).astype(F), rng)
     assert _candidate(v, s, du, np.zeros(n, dtype=F)).all()
+
+
+# ---- the general bound loop (rays without a common origin: bounce rays, shadow rays of directional lights) -----------------------
+def _general_candidate(centre32, w32, o32, du, packed):
+    """traceScene's general loop in float32 with separate roundings: oc = c - o, b = oc . du, oc2 = oc . oc;
+    scalar form:  miss = (w + 1e-6 oc2) - (oc2 - b b);   packed form (FP32 house-family kernels):  miss = b b + ((w + 1e-6 oc2) - oc2);
+    outside = w - oc2;  candidate <=> !(miss < 0 or (b < 0 and outside < 0))"""
+    oc = (centre32 - o32).astype(F)
+    b = (oc[:, 0] * du[:, 0]).astype(F)
+    b = (oc[:, 1] * du[:, 1] + b).astype(F)
+    b = (oc[:, 2] * du[:, 2] + b).astype(F)
+    oc2 = (oc[:, 0] * oc[:, 0]).astype(F)
+    oc2 = (oc[:, 1] * oc[:, 1] + oc2).astype(F)
+    oc2 = (oc[:, 2] * oc[:, 2] + oc2).astype(F)
+    t1 = (w32 + (F(1e-6) * oc2).astype(F)).astype(F)
+    bb = (b * b).astype(F)
+    if packed:
+        miss = (bb + (t1 - oc2).astype(F)).astype(F)
+    else:
+        miss = (t1 - (oc2 - bb).astype(F)).astype(F)
+    outside = (w32 - oc2).astype(F)
+    return ~((miss < 0) | ((b < 0) & (outside < 0)))
+
+
+@pytest.mark.parametrize("packed", [False, True])
+def test_general_bound_loop_never_loses_a_hit(packed):
+    """Both associations of the line-miss test keep every ray that can touch the true bound at t >= 0, from origins at all scales,
+    outside, inside and grazing; and both still cull clear misses and bounds behind the origin."""
+    rng = np.random.default_rng(23 + int(packed))
+    o = (_rand_dirs(rng, N) * 10.0 ** rng.uniform(-1, 3, size=(N, 1))).astype(F)
+    dist = 10.0 ** rng.uniform(-2, 4, size=N)
+    r = dist * 10.0 ** rng.uniform(-3, 0.3, size=N)  # up to 2 x the distance: the origin is inside some bounds
+    to_c = _rand_dirs(rng, N)
+    centre = (o.astype(np.float64) + to_c * dist[:, None]).astype(F)
+    eps = _eps(rng, N)
+    aim = centre.astype(np.float64) + _perp(rng, to_c) * (r * (1 + eps))[:, None]
+    flip = np.where(rng.random(N) < 0.15, -1.0, 1.0)  # some rays point away from the bound
+    d = (flip[:, None] * _unit(aim - o.astype(np.float64)) * rng.uniform(0.2, 3.0, size=(N, 1))).astype(F)
+    w = _inflated_r2(r)
+    cand = _general_candidate(centre, w, o, _unit32(d, rng), packed)
+    truth = _true_hit(o.astype(np.float64), d.astype(np.float64), centre.astype(np.float64), r * 1.001 + 5e-6, 0.0, np.inf)
+    assert truth.mean() > 0.3
+    lost = truth & ~cand
+    assert not lost.any(), "%d of %d true hits culled" % (lost.sum(), truth.sum())
+    b, perp2 = _line_distance(o.astype(np.float64), d.astype(np.float64), centre.astype(np.float64))
+    clear = (perp2 > (1.2 * r) ** 2) & (r > 0.1) & (dist < 50 * r)
+    assert clear.sum() > 1000 and (~cand[clear]).mean() > 0.9, (~cand[clear]).mean()
+    behind = (b < -1.01 * r * 1.002 - 1e-4) & (dist > 1.01 * r)
+    assert behind.sum() > 1000 and (~cand[behind]).all()
+    unbounded = _general_candidate(centre, np.full(N, np.inf, dtype=F), o, _unit32(d, rng), packed)
+    assert unbounded.all()  # w = +inf: neither test can fire
